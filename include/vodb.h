@@ -1,0 +1,153 @@
+/* vodb.h — C ABI of libvodb.so, the B200-native dense-retrieval hot path.
+ *
+ * This is the drop-in boundary for VOD's dynamic-retrieval path. Every entry
+ * point replaces one call the reference makes into third-party native code
+ * (faiss C++ / numba-JIT numpy); citations are relative to the reference tree.
+ *
+ *   vodb_store_create / _add        <- faiss.index_factory(D,"Flat",IP) + index.add(f32 rows)
+ *                                      src/vod_search/faiss_search/build.py:60,67-73
+ *   vodb_store_add (src_on_device)  <- the faiss-gpu sharded add_with_ids loop
+ *                                      src/vod_search/faiss_search/build_gpu.py:294-380
+ *   vodb_search                     <- faiss_index.search(query_vec, k)
+ *                                      src/vod_search/faiss_search/server.py:72,84
+ *   vodb_merge_topk                 <- the host-side IndexShards merge behind
+ *                                      faiss.index_cpu_to_all_gpus(index, co.shard=True)
+ *                                      src/vod_search/faiss_search/server.py:51-54
+ *   vodb_sample                     <- _labeled_priority_sampling_2d_ (numba)
+ *                                      src/vod_dataloaders/core/sample.py:323-352 (and :245-320, :160-219)
+ *   vodb_store_ntotal / _dim        <- index.ntotal / index.d checks, build.py:75-79; server.py:59-66
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types cross this boundary;
+ *   - every function returns 0 on success or a negative VODB_E* code; the message
+ *     is available from vodb_last_error() (thread-local);
+ *   - "on_device" flags say whether a pointer is a CUDA device pointer on the
+ *     store's device (1) or host memory (0). Host buffers are copied inside the
+ *     call (H2D of queries, D2H of results) and the call returns after the
+ *     results have landed; with device buffers the work is only enqueued on
+ *     `stream` (a cudaStream_t passed as void*, NULL = legacy default stream);
+ *   - one store = one row shard on one GPU. Multi-GPU = one process per GPU,
+ *     each owning one store with its `row_offset`; per-shard results are
+ *     exchanged by the host code (NCCL all-gather) and reduced by vodb_merge_topk;
+ *   - a store is not thread-safe: one host thread at a time.
+ */
+#ifndef VODB_H_
+#define VODB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VODB_ABI_VERSION 1
+
+/* element types of stored rows / queries */
+#define VODB_F32 0
+#define VODB_BF16 1
+#define VODB_F16 2
+
+/* scoring modes of vodb_search */
+#define VODB_MODE_EXACT 0  /* fp32 FMA on CUDA cores over the stored values: IndexFlatIP parity mode */
+#define VODB_MODE_TENSOR 1 /* tcgen05 tensor cores (bf16/fp16 store; queries rounded to the store dtype) */
+
+/* error codes */
+#define VODB_OK 0
+#define VODB_EINVAL (-1)   /* bad argument */
+#define VODB_ECUDA (-2)    /* CUDA runtime / driver error */
+#define VODB_ENOMEM (-3)   /* allocation failed */
+#define VODB_ESTATE (-4)   /* call not valid in this state (e.g. search on an empty store) */
+#define VODB_EUNSUPPORTED (-5)
+
+/* sampling quirk bits (vodb_sample `quirks`) */
+#define VODB_QUIRK_INVERTED_SUPPORT 1 /* reproduce sample.py:176-178 literally: the top
+                                          `max_support` entries are masked OUT */
+
+#define VODB_MAX_K 2048
+
+typedef struct vodb_store vodb_store;
+
+const char* vodb_last_error(void);
+int vodb_abi_version(void);
+/* number of CUDA devices visible, or a negative error code */
+int vodb_device_count(void);
+
+/* ---- corpus store ------------------------------------------------------ */
+
+/* Allocate an HBM-resident store for `n_rows` x `dim` embeddings of `dtype` on
+ * CUDA device `device`. Global ids returned by searches are row_offset + local row. */
+int vodb_store_create(vodb_store** out, int device, int64_t n_rows, int dim, int dtype,
+                      int64_t row_offset);
+void vodb_store_destroy(vodb_store* s);
+
+/* Copy rows [row0, row0+n) into the store, converting src_dtype -> store dtype
+ * (round-to-nearest-even) on the device. `rows` is row-major [n, dim]. */
+int vodb_store_add(vodb_store* s, const void* rows, int src_dtype, int src_on_device,
+                   int64_t row0, int64_t n, void* stream);
+
+/* Fill rows [row0, row0+n) with the deterministic synthetic embedding
+ * vodb_synth_value(seed, global_row, col) (csrc/vodb_math.h), generated on the device.
+ * If unit_norm != 0 rows are L2-normalised before rounding to the store dtype. */
+int vodb_store_fill_synthetic(vodb_store* s, uint64_t seed, int64_t row0, int64_t n,
+                              int unit_norm, void* stream);
+
+/* Copy rows [row0,row0+n) back out as float32 (tests / verification). */
+int vodb_store_read(vodb_store* s, int64_t row0, int64_t n, float* out, int out_on_device,
+                    void* stream);
+
+int64_t vodb_store_ntotal(const vodb_store* s); /* rows added so far (max row0+n seen) */
+int vodb_store_dim(const vodb_store* s);
+int vodb_store_dtype(const vodb_store* s);
+int vodb_store_device(const vodb_store* s);
+int64_t vodb_store_bytes(const vodb_store* s);  /* HBM bytes of the row data (pitch included) */
+
+/* ---- exact MIPS top-k --------------------------------------------------- */
+
+/* scores[q, j] = <queries[q], row(idx[q, j])>, the k largest per query, sorted by
+ * (score descending, id ascending). Slots beyond the number of stored rows get
+ * id -1 and score -FLT_MAX (what faiss returns). out_scores is float32 [nq, k],
+ * out_idx is int64 [nq, k] (global ids). 1 <= k <= VODB_MAX_K. */
+int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device, int nq,
+                int k, int mode, float* out_scores, int64_t* out_idx, int out_on_device,
+                void* stream);
+
+/* With device outputs vodb_search only enqueues work. If a per-query candidate list overflowed (adversarial
+ * row order / massive duplicate scores) a sticky device flag is set: this call synchronises `stream`, returns 1
+ * if any search since the last check overflowed (results of those searches are invalid: re-run them with host
+ * outputs, which falls back to the overflow-proof schedule), 0 if all were fine, or a negative error code. */
+int vodb_search_check(vodb_store* s, void* stream);
+
+/* Statistics of the last vodb_search on this store (for bench / tests):
+ * out[0] = number of kernel launches, out[1] = number of scan segments,
+ * out[2] = candidate-list capacity per query, out[3] = 1 if the safe fallback ran,
+ * out[4] = max candidates seen in any list, out[5..7] reserved. */
+int vodb_search_stats(const vodb_store* s, int64_t out[8]);
+
+/* Merge `n_lists` per-shard results. scores: float32 [n_lists, nq, k_in], idx:
+ * int64 [n_lists, nq, k_in] (global ids, -1 = empty slot). Writes the k_out best per
+ * query in (score desc, id asc) order. All pointers on `device` if on_device. */
+int vodb_merge_topk(int device, const float* scores, const int64_t* idx, int n_lists, int nq,
+                    int k_in, int k_out, float* out_scores, int64_t* out_idx, int on_device,
+                    void* stream);
+
+/* ---- labeled priority sampling ------------------------------------------ */
+
+/* Per row b of scores[B,K]: split entries by labels[b,:] > 0, priority-sample
+ * k_positive positives then (k_total - #positives) negatives, compute importance
+ * log-weights (self-normalised per label group if `normalized`).
+ *   noise      optional float32 [B,K] Exp(1) samples (what the reference draws from
+ *              np.random at sample.py:398); NULL -> Philox-4x32-10(seed, offset, b, j)
+ *   out_ids    int64  [B,k_total]  local column ids, -1 in unused slots
+ *   out_logw   float32[B,k_total]  -inf in unused slots
+ *   out_labels uint8  [B,k_total]
+ *   out_lse    float32[B,2]        (pos, neg) log-normalisers (sample.py:305-307)
+ * Results are bit-identical to oracle/sample_twin.c for equal inputs. K <= 8192. */
+int vodb_sample(int device, const float* scores, const uint8_t* labels, const float* noise, int B,
+                int K, int k_positive, int k_total, int normalized, float temperature,
+                int max_support, int quirks, uint64_t seed, uint64_t offset, int64_t* out_ids,
+                float* out_logw, uint8_t* out_labels, float* out_lse, int on_device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VODB_H_ */

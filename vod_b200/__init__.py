@@ -1,0 +1,21 @@
+"""vod_b200 — B200-native dense retrieval for VOD's dynamic-retrieval hot path.
+
+Exact maximum-inner-product top-k search over an HBM-resident passage-embedding store, followed by the
+dataloader's labeled priority sampling, as hand-written CUDA (sm_100a) behind the reference's own
+`vod_search` client interface and `vod_dataloaders` sampling functions. See DESIGN.md / INTEGRATION.md.
+"""
+from . import _lib
+from ._lib import VodbError, VodbUnavailableError
+from .retrieval import RetrievalBatch, RetrievalSample, RetrievalTuple
+from .sampling import (PrioritySampledSections, labeled_priority_sampling, priority_sampling_1d,
+                       sample_search_results)
+from .search import (B200SearchClient, B200SearchMaster, CorpusStore, DoNotPickleError, SearchClient,
+                     build_b200_index, merge_topk, merge_topk_device)
+from .sharded import ShardedCorpus, ShardedSearcher, shard_bounds
+
+__all__ = [
+    "B200SearchClient", "B200SearchMaster", "CorpusStore", "DoNotPickleError", "PrioritySampledSections",
+    "RetrievalBatch", "RetrievalSample", "RetrievalTuple", "SearchClient", "ShardedCorpus", "ShardedSearcher",
+    "VodbError", "VodbUnavailableError", "build_b200_index", "labeled_priority_sampling", "merge_topk",
+    "merge_topk_device", "priority_sampling_1d", "sample_search_results", "shard_bounds",
+]

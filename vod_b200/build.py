@@ -1,0 +1,81 @@
+"""Build recipe for libvodb.so (hand-written CUDA for sm_100a + the C ABI of include/vodb.h).
+
+    python -m vod_b200.build [--force]
+
+nvcc cross-compiles without a GPU. The shared library is written in-tree
+(vod_b200/libvodb.so) so that it travels to the GPU box with the repository snapshot.
+"""
+from __future__ import annotations
+
+import concurrent.futures
+import os
+import pathlib
+import shutil
+import subprocess
+import sys
+
+PKG = pathlib.Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+OBJ = PKG / "_build"
+LIB = PKG / "libvodb.so"
+SOURCES = ["api.cu", "select.cu", "score_exact.cu", "score_tc.cu", "sample.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found: libvodb.so cannot be built")
+    return cand
+
+
+def _stale(target: pathlib.Path, deps: list[pathlib.Path]) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
+    nvcc = _nvcc()
+    OBJ.mkdir(exist_ok=True)
+    headers = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [PKG.parent / "include" / "vodb.h"]
+    jobs = []
+    for src in SOURCES:
+        obj = OBJ / (src + ".o")
+        if force or _stale(obj, [CSRC / src, *headers]):
+            jobs.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        (OBJ / (src + ".log")).write_text(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        return src, r.stderr
+
+    if jobs:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for src, log in ex.map(compile_one, jobs):
+                if verbose:
+                    print(f"== {src}\n{log}")
+    objs = [OBJ / (s + ".o") for s in SOURCES]
+    if force or jobs or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
+               "-cudart", "shared"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose=True)
+    print(path)

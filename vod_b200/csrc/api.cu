@@ -1,0 +1,649 @@
+// api.cu — C ABI of libvodb.so (include/vodb.h): corpus store, search pipeline, merge, sampling.
+//
+// Search pipeline (replaces faiss `IndexFlatIP.search`, reference src/vod_search/faiss_search/server.py:84):
+//   the shard is scanned in a few geometrically growing row segments. Segment 0 appends every score to the
+//   per-query candidate lists (tau = -inf); after each segment `select` keeps the k best and publishes
+//   tau[q] = k-th best so far, so later segments append only scores >= tau[q] — for rows in random order the
+//   expected number of survivors of a segment is k * rows(segment) / rows(before), i.e. a vanishing fraction
+//   of the scores, and the [nq x rows] score matrix never exists in HBM. A list that runs out of room sets a
+//   device flag; the call then re-runs in "safe" mode (segments of cap-k rows, which cannot overflow).
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vodb {
+
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+}
+const char* get_error() { return g_error.c_str(); }
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ---- element conversion / synthetic fill kernels -----------------------------------------------
+
+template <typename S, typename D>
+__global__ void convert_rows_kernel(const S* __restrict__ src, int src_dim, D* __restrict__ dst, int dst_pitch,
+                                    int64_t n) {
+  // one thread per destination element; padded columns are written as zero
+  int64_t total = n * dst_pitch;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = e / dst_pitch;
+    int c = (int)(e - r * dst_pitch);
+    float v = (c < src_dim) ? to_f32<S>(src[r * src_dim + c]) : 0.0f;
+    dst[e] = from_f32<D>(v);
+  }
+}
+
+template <typename D>
+__device__ __forceinline__ D round_store(float v);
+template <>
+__device__ __forceinline__ float round_store<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 round_store<__nv_bfloat16>(float v) {
+  return __ushort_as_bfloat16(vodb_f32_to_bf16(v));
+}
+template <>
+__device__ __forceinline__ __half round_store<__half>(float v) { return __ushort_as_half(vodb_f32_to_f16(v)); }
+
+__global__ void synth_norm_kernel(uint64_t seed, int64_t global_row0, int64_t n, int dim, float* __restrict__ inv) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float ss = 0.0f;
+  for (int c = 0; c < dim; ++c) {
+    float v = vodb_synth_value(seed, (uint64_t)(global_row0 + r), (uint32_t)c);
+    ss = VM_ADD(ss, VM_MUL(v, v));
+  }
+  inv[r] = __fsqrt_rn(ss);
+}
+
+template <typename D>
+__global__ void synth_fill_kernel(D* __restrict__ dst, int dim, int pitch, uint64_t seed, int64_t global_row0,
+                                  int64_t n, const float* __restrict__ norms) {
+  // one thread per group of 4 columns (one Philox call)
+  const int groups = pitch / 4;
+  int64_t total = n * groups;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = e / groups;
+    int cg = (int)(e - r * groups);
+    uint64_t grow = (uint64_t)(global_row0 + r);
+    vm_u32x4 w = vodb_philox4x32((uint32_t)cg, (uint32_t)grow, (uint32_t)(grow >> 32), 0x53594e54u, (uint32_t)seed,
+                                 (uint32_t)(seed >> 32));
+    float nrm = norms ? norms[r] : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = cg * 4 + j;
+      float v = 0.0f;
+      if (c < dim) {
+        v = vodb_synth_from_word(w.v[j]);
+        if (norms && nrm > 0.0f) v = VM_DIV(v, nrm);
+      }
+      dst[r * pitch + c] = round_store<D>(v);
+    }
+  }
+}
+
+template <typename S>
+__global__ void read_rows_kernel(const S* __restrict__ src, int dim, int pitch, int64_t n, float* __restrict__ out) {
+  int64_t total = n * dim;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = e / dim;
+    int c = (int)(e - r * dim);
+    out[e] = to_f32<S>(src[r * pitch + c]);
+  }
+}
+
+inline int grid_for(int64_t total, int threads = 256) {
+  int64_t g = (total + threads - 1) / threads;
+  return (int)std::min<int64_t>(std::max<int64_t>(g, 1), 148 * 32);
+}
+
+template <typename S>
+int convert_dispatch_dst(const void* src, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
+                         cudaStream_t st) {
+  int64_t total = n * dst_pitch;
+  if (total == 0) return VODB_OK;
+  int g = grid_for(total);
+  const S* s = reinterpret_cast<const S*>(src);
+  switch (dst_dtype) {
+    case VODB_F32: convert_rows_kernel<S, float><<<g, 256, 0, st>>>(s, src_dim, (float*)dst, dst_pitch, n); break;
+    case VODB_BF16: convert_rows_kernel<S, __nv_bfloat16><<<g, 256, 0, st>>>(s, src_dim, (__nv_bfloat16*)dst, dst_pitch, n); break;
+    case VODB_F16: convert_rows_kernel<S, __half><<<g, 256, 0, st>>>(s, src_dim, (__half*)dst, dst_pitch, n); break;
+    default: set_error("bad dst dtype %d", dst_dtype); return VODB_EINVAL;
+  }
+  VODB_CUDA_CHECK(cudaGetLastError());
+  return VODB_OK;
+}
+
+}  // namespace
+
+int launch_convert_rows(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch,
+                        int64_t n, cudaStream_t st) {
+  switch (src_dtype) {
+    case VODB_F32: return convert_dispatch_dst<float>(src, src_dim, dst, dst_dtype, dst_pitch, n, st);
+    case VODB_BF16: return convert_dispatch_dst<__nv_bfloat16>(src, src_dim, dst, dst_dtype, dst_pitch, n, st);
+    case VODB_F16: return convert_dispatch_dst<__half>(src, src_dim, dst, dst_dtype, dst_pitch, n, st);
+  }
+  set_error("bad src dtype %d", src_dtype);
+  return VODB_EINVAL;
+}
+
+int launch_fill_synthetic(void* dst, int dtype, int dim, int pitch, uint64_t seed, int64_t global_row0, int64_t n,
+                          int unit_norm, cudaStream_t st) {
+  if (n == 0) return VODB_OK;
+  float* norms = nullptr;
+  if (unit_norm) {
+    VODB_CUDA_CHECK(cudaMallocAsync(&norms, (size_t)n * sizeof(float), st));
+    synth_norm_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, global_row0, n, dim, norms);
+  }
+  int g = grid_for(n * (pitch / 4));
+  switch (dtype) {
+    case VODB_F32: synth_fill_kernel<float><<<g, 256, 0, st>>>((float*)dst, dim, pitch, seed, global_row0, n, norms); break;
+    case VODB_BF16: synth_fill_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((__nv_bfloat16*)dst, dim, pitch, seed, global_row0, n, norms); break;
+    case VODB_F16: synth_fill_kernel<__half><<<g, 256, 0, st>>>((__half*)dst, dim, pitch, seed, global_row0, n, norms); break;
+    default: set_error("bad dtype %d", dtype); return VODB_EINVAL;
+  }
+  VODB_CUDA_CHECK(cudaGetLastError());
+  if (norms) VODB_CUDA_CHECK(cudaFreeAsync(norms, st));
+  return VODB_OK;
+}
+
+int launch_read_rows(const void* src, int dtype, int dim, int pitch, int64_t n, float* out, cudaStream_t st) {
+  if (n == 0) return VODB_OK;
+  int g = grid_for(n * dim);
+  switch (dtype) {
+    case VODB_F32: read_rows_kernel<float><<<g, 256, 0, st>>>((const float*)src, dim, pitch, n, out); break;
+    case VODB_BF16: read_rows_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, dim, pitch, n, out); break;
+    case VODB_F16: read_rows_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, dim, pitch, n, out); break;
+    default: set_error("bad dtype %d", dtype); return VODB_EINVAL;
+  }
+  VODB_CUDA_CHECK(cudaGetLastError());
+  return VODB_OK;
+}
+
+namespace {
+
+int pow2ceil_host(int64_t x) {
+  int64_t p = 1;
+  while (p < x) p <<= 1;
+  return (int)p;
+}
+
+// candidate-list capacity: room for ~128 k entries, within a ~4 GB budget for the whole batch
+int choose_cap(int nq, int k) {
+  int64_t cap = pow2ceil_host(std::max<int64_t>(128LL * k, 8192));
+  cap = std::min<int64_t>(cap, 65536);
+  const int64_t budget = 4LL << 30;
+  while (cap > 4LL * k && cap > 2048 && (int64_t)nq * cap * 8 > budget) cap >>= 1;
+  cap = std::max<int64_t>(cap, pow2ceil_host(4LL * k));
+  return (int)cap;
+}
+
+int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes) {
+  Workspace& w = s->ws;
+  int cap = choose_cap(nq, k);
+  if (nq > w.nq_cap || cap > w.cap) {
+    if (w.cand_s) cudaFree(w.cand_s);
+    if (w.cand_i) cudaFree(w.cand_i);
+    if (w.cnt) cudaFree(w.cnt);
+    if (w.tau) cudaFree(w.tau);
+    w.cand_s = nullptr; w.cand_i = nullptr; w.cnt = nullptr; w.tau = nullptr;
+    int nq_cap = std::max(nq, w.nq_cap);
+    int ncap = std::max(cap, w.cap);
+    VODB_CUDA_CHECK(cudaMalloc(&w.cand_s, (size_t)nq_cap * ncap * sizeof(float)));
+    VODB_CUDA_CHECK(cudaMalloc(&w.cand_i, (size_t)nq_cap * ncap * sizeof(int32_t)));
+    VODB_CUDA_CHECK(cudaMalloc(&w.cnt, (size_t)nq_cap * sizeof(int)));
+    VODB_CUDA_CHECK(cudaMalloc(&w.tau, (size_t)nq_cap * sizeof(float)));
+    w.nq_cap = nq_cap;
+    w.cap = ncap;
+  }
+  if (!w.overflow) {
+    VODB_CUDA_CHECK(cudaMalloc(&w.overflow, sizeof(int)));
+    VODB_CUDA_CHECK(cudaMemset(w.overflow, 0, sizeof(int)));
+    VODB_CUDA_CHECK(cudaMallocHost(&w.overflow_host, sizeof(int)));
+  }
+  // staged queries: rows padded to a multiple of 256 so that any TMA box is in bounds; zero filled
+  size_t rows_pad = ((size_t)nq + 255) / 256 * 256;
+  size_t need = rows_pad * (size_t)s->pitch * 4;  // big enough for fp32 or 16-bit staging
+  if (need > w.q_stage_bytes) {
+    if (w.q_stage) cudaFree(w.q_stage);
+    w.q_stage = nullptr;
+    VODB_CUDA_CHECK(cudaMalloc(&w.q_stage, need));
+    w.q_stage_bytes = need;
+  }
+  size_t need_in = (size_t)nq * s->dim * q_elem_bytes;
+  if (need_in > w.q_in_bytes) {
+    if (w.q_in) cudaFree(w.q_in);
+    w.q_in = nullptr;
+    VODB_CUDA_CHECK(cudaMalloc(&w.q_in, need_in));
+    w.q_in_bytes = need_in;
+  }
+  size_t out_need = (size_t)nq * k;
+  if (out_need > w.out_cap) {
+    if (w.out_s) cudaFree(w.out_s);
+    if (w.out_i) cudaFree(w.out_i);
+    w.out_s = nullptr; w.out_i = nullptr;
+    VODB_CUDA_CHECK(cudaMalloc(&w.out_s, out_need * sizeof(float)));
+    VODB_CUDA_CHECK(cudaMalloc(&w.out_i, out_need * sizeof(int64_t)));
+    w.out_cap = out_need;
+  }
+  return VODB_OK;
+}
+
+void free_workspace(Workspace& w) {
+  cudaFree(w.cand_s); cudaFree(w.cand_i); cudaFree(w.cnt); cudaFree(w.tau); cudaFree(w.overflow);
+  if (w.overflow_host) cudaFreeHost(w.overflow_host);
+  cudaFree(w.q_stage); cudaFree(w.q_in); cudaFree(w.out_s); cudaFree(w.out_i);
+  w = Workspace();
+}
+
+// row segments [b_i, b_{i+1}) of the scan; boundaries are multiples of 128 (except the end)
+std::vector<int64_t> plan_segments(int64_t n, int cap, int k, bool safe) {
+  std::vector<int64_t> b;
+  b.push_back(0);
+  auto round128 = [](int64_t x) { return std::max<int64_t>(128, x / 128 * 128); };
+  if (safe) {
+    int64_t step = round128(cap - k);  // cap >= 8192 > k + 128: a segment of cap-k rows cannot overflow a list
+    for (int64_t r = step; r < n; r += step) b.push_back(r);
+    b.push_back(n);
+    return b;
+  }
+  int64_t first = round128(cap / 2);
+  if (first >= n) {
+    b.push_back(n);
+    return b;
+  }
+  b.push_back(first);
+  // growth: expected survivors of a segment = k * seg/before; keep that below cap/8
+  double g = std::max(1.0, (double)cap / (8.0 * k));
+  int64_t cur = first;
+  while (cur < n) {
+    int64_t seg = round128((int64_t)(g * (double)cur));
+    int64_t nxt = cur + seg;
+    if (nxt >= n || (n - nxt) < seg / 4) nxt = n;  // fold a short tail into the last segment
+    b.push_back(nxt);
+    cur = nxt;
+  }
+  return b;
+}
+
+int run_scan(vodb_store* s, const void* q_stage, int nq, int k, int mode, bool safe, float* out_s, int64_t* out_i,
+             cudaStream_t st) {
+  Workspace& w = s->ws;
+  int rc = launch_init_lists(w.cnt, w.tau, w.overflow, nq, st);
+  if (rc != VODB_OK) return rc;
+  std::vector<int64_t> b = plan_segments(s->n_added, w.cap, k, safe);
+  int64_t launches = 1;
+  for (size_t i = 0; i + 1 < b.size(); ++i) {
+    SegmentArgs a;
+    a.corpus = s->data;
+    a.dtype = s->dtype;
+    a.pitch = s->pitch;
+    a.row_begin = b[i];
+    a.row_end = b[i + 1];
+    a.queries = q_stage;
+    a.nq = nq;
+    a.cand_s = w.cand_s;
+    a.cand_i = w.cand_i;
+    a.cnt = w.cnt;
+    a.tau = w.tau;
+    a.overflow = w.overflow;
+    a.cap = w.cap;
+    rc = (mode == VODB_MODE_TENSOR) ? launch_score_tensor(s, a, st) : launch_score_exact(a, s->sm_count, st);
+    if (rc != VODB_OK) return rc;
+    bool last = (i + 2 == b.size());
+    rc = launch_select(w.cand_s, w.cand_i, w.cnt, w.tau, w.cap, nq, k, last, out_s, out_i, s->row_offset, st);
+    if (rc != VODB_OK) return rc;
+    launches += 2;
+  }
+  s->stats[0] = launches;
+  s->stats[1] = (int64_t)b.size() - 1;
+  s->stats[2] = w.cap;
+  s->stats[3] = safe ? 1 : 0;
+  return VODB_OK;
+}
+
+}  // namespace
+
+}  // namespace vodb
+
+using namespace vodb;
+
+extern "C" {
+
+const char* vodb_last_error(void) { return get_error(); }
+int vodb_abi_version(void) { return VODB_ABI_VERSION; }
+
+int vodb_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return VODB_ECUDA;
+  }
+  return n;
+}
+
+int vodb_store_create(vodb_store** out, int device, int64_t n_rows, int dim, int dtype, int64_t row_offset) {
+  VODB_REQUIRE(out != nullptr, "vodb_store_create: out is NULL");
+  *out = nullptr;
+  VODB_REQUIRE(n_rows >= 0 && n_rows < (1LL << 31), "vodb_store_create: n_rows=%lld out of range [0, 2^31)", (long long)n_rows);
+  VODB_REQUIRE(dim > 0 && dim <= 16384, "vodb_store_create: dim=%d out of range (0, 16384]", dim);
+  VODB_REQUIRE(dtype == VODB_F32 || dtype == VODB_BF16 || dtype == VODB_F16, "vodb_store_create: bad dtype %d", dtype);
+  VODB_REQUIRE(row_offset >= 0, "vodb_store_create: negative row_offset");
+  int ndev = 0;
+  VODB_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  VODB_REQUIRE(device >= 0 && device < ndev, "vodb_store_create: device %d not in [0,%d)", device, ndev);
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    set_error("cudaSetDevice(%d) failed", device);
+    return VODB_ECUDA;
+  }
+  vodb_store* s = new (std::nothrow) vodb_store();
+  if (!s) {
+    set_error("out of host memory");
+    return VODB_ENOMEM;
+  }
+  s->device = device;
+  s->n_rows = n_rows;
+  s->dim = dim;
+  s->pitch = (dim + kPitchAlign - 1) / kPitchAlign * kPitchAlign;
+  s->dtype = dtype;
+  s->row_offset = row_offset;
+  cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
+  size_t bytes = (size_t)std::max<int64_t>(n_rows, 1) * s->pitch * dtype_size(dtype);
+  cudaError_t e = cudaMalloc(&s->data, bytes);
+  if (e != cudaSuccess) {
+    set_error("vodb_store_create: cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    delete s;
+    cudaGetLastError();
+    return VODB_ENOMEM;
+  }
+  *out = s;
+  return VODB_OK;
+}
+
+void vodb_store_destroy(vodb_store* s) {
+  if (!s) return;
+  DeviceGuard guard(s->device);
+  cudaDeviceSynchronize();
+  free_workspace(s->ws);
+  if (s->stage) cudaFree(s->stage);
+  if (s->data) cudaFree(s->data);
+  delete s;
+}
+
+int vodb_store_add(vodb_store* s, const void* rows, int src_dtype, int src_on_device, int64_t row0, int64_t n,
+                   void* stream) {
+  VODB_REQUIRE(s != nullptr, "vodb_store_add: store is NULL");
+  VODB_REQUIRE(n >= 0 && row0 >= 0 && row0 + n <= s->n_rows, "vodb_store_add: rows [%lld, %lld) outside the store (%lld rows)",
+               (long long)row0, (long long)(row0 + n), (long long)s->n_rows);
+  VODB_REQUIRE(src_dtype == VODB_F32 || src_dtype == VODB_BF16 || src_dtype == VODB_F16, "vodb_store_add: bad src dtype %d", src_dtype);
+  if (n == 0) return VODB_OK;
+  VODB_REQUIRE(rows != nullptr, "vodb_store_add: rows is NULL");
+  DeviceGuard guard(s->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t esz = dtype_size(src_dtype);
+  char* dst = reinterpret_cast<char*>(s->data) + (size_t)row0 * s->pitch * dtype_size(s->dtype);
+  if (src_on_device) {
+    int rc = launch_convert_rows(rows, src_dtype, s->dim, dst, s->dtype, s->pitch, n, st);
+    if (rc != VODB_OK) return rc;
+  } else {
+    // chunked upload through a device staging buffer (64 MiB), converted on the device
+    const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / ((size_t)s->dim * esz));
+    size_t need = std::min<size_t>((size_t)n, chunk_rows) * s->dim * esz;
+    if (need > s->stage_bytes) {
+      if (s->stage) cudaFree(s->stage);
+      s->stage = nullptr;
+      VODB_CUDA_CHECK(cudaMalloc(&s->stage, need));
+      s->stage_bytes = need;
+    }
+    for (int64_t r = 0; r < n; r += (int64_t)chunk_rows) {
+      int64_t m = std::min<int64_t>((int64_t)chunk_rows, n - r);
+      const char* src = reinterpret_cast<const char*>(rows) + (size_t)r * s->dim * esz;
+      VODB_CUDA_CHECK(cudaMemcpyAsync(s->stage, src, (size_t)m * s->dim * esz, cudaMemcpyHostToDevice, st));
+      int rc = launch_convert_rows(s->stage, src_dtype, s->dim, dst + (size_t)r * s->pitch * dtype_size(s->dtype),
+                                   s->dtype, s->pitch, m, st);
+      if (rc != VODB_OK) return rc;
+      VODB_CUDA_CHECK(cudaStreamSynchronize(st));  // the staging buffer is reused by the next chunk
+    }
+  }
+  s->n_added = std::max(s->n_added, row0 + n);
+  return VODB_OK;
+}
+
+int vodb_store_fill_synthetic(vodb_store* s, uint64_t seed, int64_t row0, int64_t n, int unit_norm, void* stream) {
+  VODB_REQUIRE(s != nullptr, "vodb_store_fill_synthetic: store is NULL");
+  VODB_REQUIRE(n >= 0 && row0 >= 0 && row0 + n <= s->n_rows, "vodb_store_fill_synthetic: rows outside the store");
+  DeviceGuard guard(s->device);
+  char* dst = reinterpret_cast<char*>(s->data) + (size_t)row0 * s->pitch * dtype_size(s->dtype);
+  int rc = launch_fill_synthetic(dst, s->dtype, s->dim, s->pitch, seed, s->row_offset + row0, n, unit_norm,
+                                 reinterpret_cast<cudaStream_t>(stream));
+  if (rc != VODB_OK) return rc;
+  s->n_added = std::max(s->n_added, row0 + n);
+  return VODB_OK;
+}
+
+int vodb_store_read(vodb_store* s, int64_t row0, int64_t n, float* out, int out_on_device, void* stream) {
+  VODB_REQUIRE(s != nullptr && out != nullptr, "vodb_store_read: NULL argument");
+  VODB_REQUIRE(n >= 0 && row0 >= 0 && row0 + n <= s->n_rows, "vodb_store_read: rows outside the store");
+  if (n == 0) return VODB_OK;
+  DeviceGuard guard(s->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const char* src = reinterpret_cast<const char*>(s->data) + (size_t)row0 * s->pitch * dtype_size(s->dtype);
+  if (out_on_device) return launch_read_rows(src, s->dtype, s->dim, s->pitch, n, out, st);
+  float* tmp = nullptr;
+  VODB_CUDA_CHECK(cudaMalloc(&tmp, (size_t)n * s->dim * sizeof(float)));
+  int rc = launch_read_rows(src, s->dtype, s->dim, s->pitch, n, tmp, st);
+  if (rc == VODB_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)n * s->dim * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      set_error("vodb_store_read: %s", cudaGetErrorString(e));
+      rc = VODB_ECUDA;
+    }
+  }
+  cudaFree(tmp);
+  return rc;
+}
+
+int64_t vodb_store_ntotal(const vodb_store* s) { return s ? s->n_added : 0; }
+int vodb_store_dim(const vodb_store* s) { return s ? s->dim : 0; }
+int vodb_store_dtype(const vodb_store* s) { return s ? s->dtype : -1; }
+int vodb_store_device(const vodb_store* s) { return s ? s->device : -1; }
+int64_t vodb_store_bytes(const vodb_store* s) {
+  return s ? (int64_t)s->n_added * s->pitch * dtype_size(s->dtype) : 0;
+}
+
+int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device, int nq, int k, int mode,
+                float* out_scores, int64_t* out_idx, int out_on_device, void* stream) {
+  VODB_REQUIRE(s != nullptr, "vodb_search: store is NULL");
+  VODB_REQUIRE(queries != nullptr || nq == 0, "vodb_search: queries is NULL");
+  VODB_REQUIRE(nq >= 0, "vodb_search: nq=%d < 0", nq);
+  VODB_REQUIRE(k >= 1 && k <= VODB_MAX_K, "vodb_search: k=%d outside [1, %d]", k, VODB_MAX_K);
+  VODB_REQUIRE(q_dtype == VODB_F32 || q_dtype == VODB_BF16 || q_dtype == VODB_F16, "vodb_search: bad query dtype %d", q_dtype);
+  VODB_REQUIRE(mode == VODB_MODE_EXACT || mode == VODB_MODE_TENSOR, "vodb_search: bad mode %d", mode);
+  if (nq == 0) return VODB_OK;
+  VODB_REQUIRE(out_scores != nullptr && out_idx != nullptr, "vodb_search: output pointer is NULL");
+  if (s->n_added <= 0) {
+    set_error("vodb_search: the store is empty (faiss health check: 'ERROR: Index is empty')");
+    return VODB_ESTATE;
+  }
+  if (mode == VODB_MODE_TENSOR && !tensor_path_supported(s)) {
+    set_error("vodb_search: VODB_MODE_TENSOR needs a bf16/f16 store and a driver exporting cuTensorMapEncodeTiled");
+    return VODB_EUNSUPPORTED;
+  }
+  DeviceGuard guard(s->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = ensure_workspace(s, nq, k, dtype_size(q_dtype));
+  if (rc != VODB_OK) return rc;
+  Workspace& w = s->ws;
+
+  // stage queries: host -> device copy if needed, then convert/pad to [nq_pad, pitch] of the scoring dtype
+  const void* q_dev = queries;
+  if (!q_on_device) {
+    VODB_CUDA_CHECK(cudaMemcpyAsync(w.q_in, queries, (size_t)nq * s->dim * dtype_size(q_dtype), cudaMemcpyHostToDevice, st));
+    q_dev = w.q_in;
+  }
+  const int stage_dtype = (mode == VODB_MODE_TENSOR) ? s->dtype : VODB_F32;
+  size_t rows_pad = ((size_t)nq + 255) / 256 * 256;
+  VODB_CUDA_CHECK(cudaMemsetAsync(w.q_stage, 0, rows_pad * s->pitch * dtype_size(stage_dtype), st));
+  rc = launch_convert_rows(q_dev, q_dtype, s->dim, w.q_stage, stage_dtype, s->pitch, nq, st);
+  if (rc != VODB_OK) return rc;
+
+  float* o_s = out_on_device ? out_scores : w.out_s;
+  int64_t* o_i = out_on_device ? out_idx : w.out_i;
+  if (out_on_device) {
+    // asynchronous: only enqueue. A list overflow leaves the sticky device flag set; the caller polls it
+    // with vodb_search_check() (bench / pipelined callers) and re-runs synchronously if it fired.
+    return run_scan(s, w.q_stage, nq, k, mode, /*safe=*/false, o_s, o_i, st);
+  }
+  bool safe = false;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    rc = run_scan(s, w.q_stage, nq, k, mode, safe, o_s, o_i, st);
+    if (rc != VODB_OK) return rc;
+    VODB_CUDA_CHECK(cudaMemcpyAsync(w.overflow_host, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VODB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (*w.overflow_host == 0) break;
+    VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
+    if (safe) {
+      set_error("vodb_search: candidate list overflow in safe mode (internal error)");
+      return VODB_ESTATE;
+    }
+    safe = true;  // re-run with segments that cannot overflow
+  }
+  if (!out_on_device) {
+    VODB_CUDA_CHECK(cudaMemcpyAsync(out_scores, w.out_s, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    VODB_CUDA_CHECK(cudaMemcpyAsync(out_idx, w.out_i, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VODB_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  return VODB_OK;
+}
+
+int vodb_search_check(vodb_store* s, void* stream) {
+  VODB_REQUIRE(s != nullptr, "vodb_search_check: store is NULL");
+  Workspace& w = s->ws;
+  if (!w.overflow) return 0;
+  DeviceGuard guard(s->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VODB_CUDA_CHECK(cudaMemcpyAsync(w.overflow_host, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+  VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
+  VODB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return *w.overflow_host != 0 ? 1 : 0;
+}
+
+int vodb_search_stats(const vodb_store* s, int64_t out[8]) {
+  VODB_REQUIRE(s != nullptr && out != nullptr, "vodb_search_stats: NULL argument");
+  std::memcpy(out, s->stats, sizeof(s->stats));
+  return VODB_OK;
+}
+
+int vodb_merge_topk(int device, const float* scores, const int64_t* idx, int n_lists, int nq, int k_in, int k_out,
+                    float* out_scores, int64_t* out_idx, int on_device, void* stream) {
+  VODB_REQUIRE(n_lists >= 1 && nq >= 0 && k_in >= 1 && k_out >= 1 && k_out <= VODB_MAX_K, "vodb_merge_topk: bad sizes");
+  VODB_REQUIRE((int64_t)n_lists * k_in <= (1 << 20), "vodb_merge_topk: n_lists*k_in too large");
+  if (nq == 0) return VODB_OK;
+  VODB_REQUIRE(scores && idx && out_scores && out_idx, "vodb_merge_topk: NULL pointer");
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    set_error("cudaSetDevice(%d) failed", device);
+    return VODB_ECUDA;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (on_device) return launch_merge(scores, idx, n_lists, nq, k_in, k_out, out_scores, out_idx, st);
+  size_t n_in = (size_t)n_lists * nq * k_in, n_out = (size_t)nq * k_out;
+  float *d_s = nullptr, *d_os = nullptr;
+  int64_t *d_i = nullptr, *d_oi = nullptr;
+  int rc = VODB_OK;
+  cudaError_t e = cudaMalloc(&d_s, n_in * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_i, n_in * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_os, n_out * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_oi, n_out * 8);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, scores, n_in * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, idx, n_in * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) rc = launch_merge(d_s, d_i, n_lists, nq, k_in, k_out, d_os, d_oi, st);
+  if (e == cudaSuccess && rc == VODB_OK) e = cudaMemcpyAsync(out_scores, d_os, n_out * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == VODB_OK) e = cudaMemcpyAsync(out_idx, d_oi, n_out * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_s); cudaFree(d_i); cudaFree(d_os); cudaFree(d_oi);
+  if (e != cudaSuccess) {
+    set_error("vodb_merge_topk: %s", cudaGetErrorString(e));
+    return VODB_ECUDA;
+  }
+  return rc;
+}
+
+int vodb_sample(int device, const float* scores, const uint8_t* labels, const float* noise, int B, int K,
+                int k_positive, int k_total, int normalized, float temperature, int max_support, int quirks,
+                uint64_t seed, uint64_t offset, int64_t* out_ids, float* out_logw, uint8_t* out_labels,
+                float* out_lse, int on_device, void* stream) {
+  VODB_REQUIRE(B >= 0 && K >= 0, "vodb_sample: negative shape");
+  VODB_REQUIRE(K <= 8192, "vodb_sample: K=%d > 8192", K);
+  VODB_REQUIRE(k_total >= 0 && k_positive >= 0 && k_positive <= k_total, "vodb_sample: need 0 <= k_positive <= k_total (got %d, %d)", k_positive, k_total);
+  if (B == 0) return VODB_OK;
+  VODB_REQUIRE(scores && out_ids && out_logw && out_labels && out_lse, "vodb_sample: NULL pointer");
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    set_error("cudaSetDevice(%d) failed", device);
+    return VODB_ECUDA;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (on_device)
+    return launch_sample(scores, labels, noise, B, K, k_positive, k_total, normalized, temperature, max_support,
+                         quirks, seed, offset, out_ids, out_logw, out_labels, out_lse, st);
+  // host buffers: one packed device allocation
+  size_t nBK = (size_t)B * K, nBk = (size_t)B * k_total;
+  size_t off_scores = 0, off_noise = off_scores + nBK * 4, off_logw = off_noise + (noise ? nBK * 4 : 0);
+  size_t off_lse = off_logw + nBk * 4, off_ids = (off_lse + (size_t)B * 8 + 7) / 8 * 8;
+  size_t off_labels = off_ids + nBk * 8, off_olab = off_labels + (labels ? nBK : 0), total = off_olab + nBk + 16;
+  char* d = nullptr;
+  VODB_CUDA_CHECK(cudaMalloc(&d, total));
+  int rc = VODB_OK;
+  cudaError_t e = cudaMemcpyAsync(d + off_scores, scores, nBK * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && noise) e = cudaMemcpyAsync(d + off_noise, noise, nBK * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && labels) e = cudaMemcpyAsync(d + off_labels, labels, nBK, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    rc = launch_sample((const float*)(d + off_scores), labels ? (const uint8_t*)(d + off_labels) : nullptr,
+                       noise ? (const float*)(d + off_noise) : nullptr, B, K, k_positive, k_total, normalized,
+                       temperature, max_support, quirks, seed, offset, (int64_t*)(d + off_ids), (float*)(d + off_logw),
+                       (uint8_t*)(d + off_olab), (float*)(d + off_lse), st);
+  if (e == cudaSuccess && rc == VODB_OK && nBk) {
+    e = cudaMemcpyAsync(out_ids, d + off_ids, nBk * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_logw, d + off_logw, nBk * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_labels, d + off_olab, nBk, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess && rc == VODB_OK) e = cudaMemcpyAsync(out_lse, d + off_lse, (size_t)B * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) {
+    set_error("vodb_sample: %s", cudaGetErrorString(e));
+    return VODB_ECUDA;
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+// common.cuh — shared declarations of libvodb.so (internal; the public ABI is include/vodb.h)
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/vodb.h"
+#include "vodb_math.h"
+
+namespace vodb {
+
+// ---- errors -----------------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define VODB_CUDA_CHECK(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ::vodb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return VODB_ECUDA;                                                                   \
+    }                                                                                      \
+  } while (0)
+
+#define VODB_REQUIRE(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::vodb::set_error(__VA_ARGS__);    \
+      return VODB_EINVAL;                \
+    }                                    \
+  } while (0)
+
+// ---- element types ------------------------------------------------------------
+__host__ __device__ inline int dtype_size(int dtype) { return dtype == VODB_F32 ? 4 : 2; }
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// order-preserving float -> uint32 (bigger float = bigger uint); NaN lowest; -0 == +0
+__host__ __device__ __forceinline__ uint32_t ord_u32(float x) {
+  uint32_t u = vm_f2u(x);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0u;
+  if ((u & 0x7fffffffu) == 0u) u = 0u;
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord_to_float(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return vm_u2f(u);
+}
+
+#define VODB_NEG_FLT_MAX (-3.402823466e+38f)
+
+// ---- corpus store ---------------------------------------------------------------
+constexpr int kPitchAlign = 64;  // elements; one 128-byte TMA swizzle atom of 2-byte types
+
+struct Workspace {
+  // per-query candidate lists: scores/ids [nq_cap, cap], counts, thresholds
+  float* cand_s = nullptr;
+  int32_t* cand_i = nullptr;
+  int* cnt = nullptr;
+  float* tau = nullptr;
+  int* overflow = nullptr;     // device flag: a candidate list ran out of room
+  int* overflow_host = nullptr;  // pinned mirror
+  int nq_cap = 0;
+  int cap = 0;
+  // staged queries (converted / padded) and staged outputs for host callers
+  void* q_stage = nullptr;
+  size_t q_stage_bytes = 0;
+  void* q_in = nullptr;  // raw copy of host queries
+  size_t q_in_bytes = 0;
+  float* out_s = nullptr;
+  int64_t* out_i = nullptr;
+  size_t out_cap = 0;  // elements
+};
+
+}  // namespace vodb
+
+struct vodb_store {
+  int device = 0;
+  int64_t n_rows = 0;      // capacity
+  int64_t n_added = 0;     // rows filled so far
+  int dim = 0;
+  int pitch = 0;           // elements per stored row (dim rounded up to kPitchAlign)
+  int dtype = VODB_F32;
+  int64_t row_offset = 0;
+  void* data = nullptr;    // [n_rows, pitch] of dtype, zero padded
+  int sm_count = 0;
+  vodb::Workspace ws;
+  void* stage = nullptr;   // staging buffer for host->device adds
+  size_t stage_bytes = 0;
+  // TMA descriptor cache for the tensor-core path (opaque CUtensorMap storage)
+  alignas(64) unsigned char tmap_corpus[128];
+  bool tmap_corpus_valid = false;
+  int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace vodb {
+
+// ---- kernels launched by the search pipeline (defined in the .cu files) ----------
+struct SegmentArgs {
+  const void* corpus;   // [n_rows, pitch]
+  int dtype;
+  int pitch;
+  int64_t row_begin;    // segment [row_begin, row_end) of local rows
+  int64_t row_end;
+  const void* queries;  // EXACT: float32 [nq, pitch]; TENSOR: store dtype [nq_pad, pitch]
+  int nq;
+  float* cand_s;
+  int32_t* cand_i;
+  int* cnt;
+  const float* tau;
+  int* overflow;
+  int cap;
+};
+
+int launch_score_exact(const SegmentArgs& a, int sm_count, cudaStream_t stream);
+int launch_score_tensor(vodb_store* s, const SegmentArgs& a, cudaStream_t stream);
+bool tensor_path_supported(const vodb_store* s);
+
+// select the k best candidates of every query list; if `final`, sort and write outputs
+int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap, int nq, int k, bool final,
+                  float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream);
+int launch_merge(const float* scores, const int64_t* idx, int n_lists, int nq, int k_in, int k_out, float* out_s,
+                 int64_t* out_i, cudaStream_t stream);
+int launch_init_lists(int* cnt, float* tau, int* overflow, int nq, cudaStream_t stream);
+
+int launch_convert_rows(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch,
+                        int64_t n, cudaStream_t stream);
+int launch_fill_synthetic(void* dst, int dtype, int dim, int pitch, uint64_t seed, int64_t global_row0, int64_t n,
+                          int unit_norm, cudaStream_t stream);
+int launch_read_rows(const void* src, int dtype, int dim, int pitch, int64_t n, float* out, cudaStream_t stream);
+
+int launch_sample(const float* scores, const uint8_t* labels, const float* noise, int B, int K, int k_positive,
+                  int k_total, int normalized, float temperature, int max_support, int quirks, uint64_t seed,
+                  uint64_t offset, int64_t* out_ids, float* out_logw, uint8_t* out_labels, float* out_lse,
+                  cudaStream_t stream);
+
+}  // namespace vodb

@@ -1,0 +1,432 @@
+// score_tc.cu — tensor-core scoring (tcgen05 + TMA + TMEM) fused with the top-k candidate filter.
+//
+// Replaces the scoring half of `faiss_index.search(query_vec, k)` when the index is served from GPUs
+// (reference src/vod_search/faiss_search/server.py:51-54,84: GpuIndexFlat shards with useFloat16 storage,
+// src/vod_configs/search.py:52,71 — cuBLAS GEMM + faiss k-select, score matrix through HBM). Here the
+// [corpus rows x queries] score tile lives only in TMEM:
+//
+//   warp 0 (1 thread)  TMA producer: streams 128-row x 64-col corpus boxes and BN-row x 64-col query boxes
+//                      (128-byte swizzle) through a STAGES-deep mbarrier ring;
+//   warp 1 (1 thread)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 (corpus rows), N=BN (queries),
+//                      K=16 per instruction, fp32 accumulation in one of two TMEM accumulator buffers;
+//   warps 2..5         epilogue: tcgen05.ld 32 lanes x 32 columns, compare every score with the query's
+//                      running threshold tau[q] (k-th best so far, select.cu) and append the rare survivors
+//                      to the per-query candidate list with one warp-aggregated atomic.
+//
+// D (accumulator) row i = TMEM lane i = corpus row; column j = query j of the tile. Persistent CTAs
+// (one per SM) walk (corpus tile, query tile) items with the query tile fastest, so that co-resident CTAs
+// share the same corpus tile in L2 when nq > BN.
+//
+// Algorithmic work per segment: rows*pitch*2 bytes from HBM, 2*nq*rows*pitch flop.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace vodb {
+
+namespace {
+
+constexpr int BM = 128;       // corpus rows per MMA (M)
+constexpr int KC = 64;        // K elements per pipeline stage (128 bytes = one swizzle atom)
+constexpr int UMMA_K = 16;    // K per tcgen05.mma for 16-bit inputs
+constexpr int kThreads = 192; // 6 warps
+constexpr uint32_t kSmemBudget = 200 * 1024;
+
+// L2 cache-policy descriptors (cute::TMA::CacheHintSm90 values)
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (error code at the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("vodb: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, (void*)bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, void* smem_dst, int c0, int c1,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, 16-bit inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start address>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)1 << 16;               // LBO (unused for swizzled K-major; canonical value 1)
+  d |= (uint64_t)(1024 >> 4) << 32;     // SBO: 8 rows x 128 B between 8-row core-matrix groups
+  d |= (uint64_t)1 << 46;               // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;               // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct TcParams {
+  int64_t row_begin, row_end;
+  int nq;
+  int n_ctiles, n_qtiles;
+  int kchunks;  // pitch / KC
+  float* cand_s;
+  int32_t* cand_i;
+  int* cnt;
+  const float* tau;
+  int* overflow;
+  int cap;
+  uint32_t idesc;
+};
+
+template <int BN>
+struct TcConfig {
+  static constexpr uint32_t kABytes = BM * KC * 2;
+  static constexpr uint32_t kBBytes = BN * KC * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                        : (2 * BN <= 256) ? 256 : 512;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                         2 * BN * sizeof(float) /*tau*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_constant__ CUtensorMap tmap_query,
+                const TcParams p) {
+  using Cfg = TcConfig<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment is required by the 128-byte swizzle (TMA writes and UMMA reads XOR address bits [4,7) with [7,10))
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;                                   // STAGES x [128 x 128B]
+  unsigned char* smem_b = smem + STAGES * Cfg::kABytes;           // STAGES x [BN x 128B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* tau_s = reinterpret_cast<float*>(bars + 2 * STAGES + 6);  // [2][BN]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = p.n_ctiles * p.n_qtiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_corpus) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_query) : "memory");
+      const uint64_t corpus_policy = (p.n_qtiles == 1) ? kEvictFirst : kEvictLast;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int ct = item / p.n_qtiles, qt = item - ct * p.n_qtiles;
+        const int row0 = (int)(p.row_begin + (int64_t)ct * BM);
+        const int q0 = qt * BN;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC, row0, corpus_policy);
+          tma_load_2d(&tmap_query, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kc * KC, q0, kEvictLast);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator buffer
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
+          tcgen05_fence_after();
+          const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = make_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < KC / UMMA_K; ++k) {
+            // advance 32 bytes (16 elements) inside the 128-byte swizzle atom: +2 in the >>4 address field
+            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once the MMAs above have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ---------------- epilogue warps (2..5) ----------------
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 64;  // 0..127
+    int local = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+      const int ct = item / p.n_qtiles, qt = item - ct * p.n_qtiles;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int q0 = qt * BN;
+      float* tau_cur = tau_s + acc * BN;
+      // stage this query tile's thresholds (queries past nq never pass)
+      for (int c = et; c < BN; c += 128) tau_cur[c] = (q0 + c < p.nq) ? p.tau[q0 + c] : INFINITY;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      const int64_t row = p.row_begin + (int64_t)ct * BM + quarter * 32 + lane;
+      const bool valid = row < p.row_end;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr0 + (uint32_t)c0, v);
+        tmem_ld_wait();
+        bool any = false;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 t = *reinterpret_cast<const float4*>(tau_cur + c0 + j4 * 4);
+          any |= (__uint_as_float(v[j4 * 4 + 0]) >= t.x) | (__uint_as_float(v[j4 * 4 + 1]) >= t.y) |
+                 (__uint_as_float(v[j4 * 4 + 2]) >= t.z) | (__uint_as_float(v[j4 * 4 + 3]) >= t.w);
+        }
+        any = any && valid;
+        if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float s = __uint_as_float(v[j]);
+            const bool pass = valid && (s >= tau_cur[c0 + j]);
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (m != 0u) {
+              const int q = q0 + c0 + j;
+              const int leader = __ffs(m) - 1;
+              int base = 0;
+              if (lane == leader) base = atomicAdd(&p.cnt[q], __popc(m));
+              base = __shfl_sync(0xffffffffu, base, leader);
+              if (pass) {
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                if (pos < p.cap) {
+                  p.cand_s[(size_t)q * p.cap + pos] = s;
+                  p.cand_i[(size_t)q * p.cap + pos] = (int32_t)row;
+                } else {
+                  *p.overflow = 1;
+                }
+              }
+            }
+          }
+        }
+      }
+      // all TMEM reads of this buffer are complete (wait::ld above): hand it back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2D row-major [rows, pitch] tensor of 16-bit elements, box = [box_rows, 64 cols], 128B swizzle
+int encode_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int pitch, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return VODB_EUNSUPPORTED;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = dtype == VODB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld pitch=%d box_rows=%d)", (int)r,
+              (long long)rows, pitch, box_rows);
+    return VODB_ECUDA;
+  }
+  return VODB_OK;
+}
+
+template <int BN>
+int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
+  using Cfg = TcConfig<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VODB_CUDA_CHECK(cudaFuncSetAttribute(score_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  if (!s->tmap_corpus_valid) {
+    int rc = encode_2d(reinterpret_cast<CUtensorMap*>(s->tmap_corpus), s->data, s->dtype, s->n_rows, s->pitch, BM);
+    if (rc != VODB_OK) return rc;
+    s->tmap_corpus_valid = true;
+  }
+  alignas(64) CUtensorMap tmap_q;
+  int rc = encode_2d(&tmap_q, a.queries, s->dtype, a.nq, s->pitch, BN);
+  if (rc != VODB_OK) return rc;
+
+  TcParams p;
+  p.row_begin = a.row_begin;
+  p.row_end = a.row_end;
+  p.nq = a.nq;
+  p.n_ctiles = (int)((a.row_end - a.row_begin + BM - 1) / BM);
+  p.n_qtiles = (a.nq + BN - 1) / BN;
+  p.kchunks = s->pitch / KC;
+  p.cand_s = a.cand_s;
+  p.cand_i = a.cand_i;
+  p.cnt = a.cnt;
+  p.tau = a.tau;
+  p.overflow = a.overflow;
+  p.cap = a.cap;
+  const uint32_t fmt = (s->dtype == VODB_BF16) ? 1u : 0u;  // UMMA F16F32Format: F16=0, BF16=1
+  p.idesc = (1u << 4) /*D=f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
+  if (items <= 0) return VODB_OK;
+  int grid = (int)(items < s->sm_count ? items : s->sm_count);
+  score_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(*reinterpret_cast<CUtensorMap*>(s->tmap_corpus),
+                                                                   tmap_q, p);
+  VODB_CUDA_CHECK(cudaGetLastError());
+  return VODB_OK;
+}
+
+}  // namespace
+
+bool tensor_path_supported(const vodb_store* s) {
+  return (s->dtype == VODB_BF16 || s->dtype == VODB_F16) && get_encode_fn() != nullptr;
+}
+
+int launch_score_tensor(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
+  if (a.row_begin % BM != 0) {
+    set_error("launch_score_tensor: segment start %lld is not a multiple of %d", (long long)a.row_begin, BM);
+    return VODB_EINVAL;
+  }
+  if ((int64_t)s->n_rows > 0x7fffffffLL) {
+    set_error("launch_score_tensor: shard too large for 32-bit TMA coordinates");
+    return VODB_EUNSUPPORTED;
+  }
+  if (a.nq <= 64) return launch_bn<64>(s, a, stream);
+  if (a.nq <= 128) return launch_bn<128>(s, a, stream);
+  return launch_bn<256>(s, a, stream);
+}
+
+}  // namespace vodb

@@ -1,0 +1,309 @@
+// select.cu — per-query exact top-k selection over candidate lists (radix select + bitonic sort).
+//
+// Replaces the k-selection half of faiss' IndexFlat::search (heap / reservoir collection behind
+// `faiss_index.search`, reference src/vod_search/faiss_search/server.py:84) and, as `merge`, the
+// host-side IndexShards merge behind `faiss.index_cpu_to_all_gpus(..., co.shard=True)` (server.py:51-54).
+//
+// One CTA per query. The list is a bag of (score, id) pairs appended by the scoring kernels.
+//   1. 4-pass (8 bits each) MSB radix select on the order-preserving uint32 image of the score finds
+//      v* = the k-th largest score and how many entries tied at v* are needed;
+//   2. if the tie group is larger than needed, a second radix select picks the smallest ids;
+//   3. the selected entries are compacted into shared memory; when `final`, a bitonic network sorts
+//      them by (score desc, id asc) and writes scores / global ids, else they are written back to the
+//      front of the list and tau[q] := v* becomes the filter threshold of the next scan segment.
+// Exact (no approximation): the order is total because ids are unique within a list.
+#include "common.cuh"
+
+namespace vodb {
+
+namespace {
+
+constexpr int kSelThreads = 256;
+
+template <typename IdxT>
+struct UIdx;
+template <>
+struct UIdx<int32_t> { using type = uint32_t; };
+template <>
+struct UIdx<int64_t> { using type = uint64_t; };
+
+template <typename IdxT>
+struct SelectSmem {
+  int hist[256];
+  int bin;
+  int need;
+  int n_eq;
+  int sel_count;
+  int dup_taken;
+  uint32_t min_ord;
+};
+
+// (o desc, uidx asc) "a before b"
+template <typename U>
+__device__ __forceinline__ bool before(uint32_t oa, U ia, uint32_t ob, U ib) {
+  return (oa > ob) || (oa == ob && ia < ib);
+}
+
+// Core routine. load(i, score, idx) reads entry i in [0,n). Results: sel_o/sel_i[0..n_sel) in shared
+// memory (sorted if do_sort), returns n_sel = min(n,k); *vstar_out = ord image of the k-th best score
+// (0 if n < k).
+template <typename IdxT, typename Loader>
+__device__ int block_select(Loader load, int n, int k, bool do_sort, SelectSmem<IdxT>& sm, uint32_t* sel_o,
+                            IdxT* sel_i, int P, uint32_t* vstar_out) {
+  using U = typename UIdx<IdxT>::type;
+  const int tid = threadIdx.x;
+  const int nt = blockDim.x;
+  int n_sel;
+  uint32_t vstar = 0u;
+
+  if (n <= k) {
+    if (tid == 0) sm.min_ord = 0xffffffffu;
+    __syncthreads();
+    uint32_t local_min = 0xffffffffu;
+    for (int i = tid; i < n; i += nt) {
+      float s;
+      IdxT id;
+      load(i, s, id);
+      uint32_t o = ord_u32(s);
+      sel_o[i] = o;
+      sel_i[i] = id;
+      local_min = min(local_min, o);
+    }
+    atomicMin(&sm.min_ord, local_min);
+    __syncthreads();
+    n_sel = n;
+    vstar = (n == k && n > 0) ? sm.min_ord : 0u;
+  } else {
+    uint32_t prefix = 0u, mask = 0u;
+    int need = k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int t = tid; t < 256; t += nt) sm.hist[t] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += nt) {
+        float s;
+        IdxT id;
+        load(i, s, id);
+        uint32_t o = ord_u32(s);
+        if ((o & mask) == prefix) atomicAdd(&sm.hist[(o >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, b = 255;
+        for (; b > 0; --b) {
+          int h = sm.hist[b];
+          if (cum + h >= need) break;
+          cum += h;
+        }
+        sm.bin = b;
+        sm.need = need - cum;
+        sm.n_eq = sm.hist[b];
+      }
+      __syncthreads();
+      prefix |= (uint32_t)sm.bin << shift;
+      mask |= 0xffu << shift;
+      need = sm.need;
+      __syncthreads();
+    }
+    vstar = prefix;
+    const int n_eq = sm.n_eq;
+    // ties at v*: take the `need` smallest ids
+    U istar = ~(U)0;
+    int ineed = 0x7fffffff;  // how many entries with (o==v*, id==istar) to take
+    if (n_eq > need) {
+      U iprefix = 0, imask = 0;
+      ineed = need;
+      for (int shift = (int)sizeof(U) * 8 - 8; shift >= 0; shift -= 8) {
+        for (int t = tid; t < 256; t += nt) sm.hist[t] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += nt) {
+          float s;
+          IdxT id;
+          load(i, s, id);
+          if (ord_u32(s) == vstar && (((U)id) & imask) == iprefix) atomicAdd(&sm.hist[(int)((((U)id) >> shift) & 255u)], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int cum = 0, b = 0;
+          for (; b < 255; ++b) {
+            int h = sm.hist[b];
+            if (cum + h >= ineed) break;
+            cum += h;
+          }
+          sm.bin = b;
+          sm.need = ineed - cum;
+        }
+        __syncthreads();
+        iprefix |= (U)sm.bin << shift;
+        imask |= (U)0xff << shift;
+        ineed = sm.need;
+        __syncthreads();
+      }
+      istar = iprefix;
+    }
+    if (tid == 0) {
+      sm.sel_count = 0;
+      sm.dup_taken = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+      float s;
+      IdxT id;
+      load(i, s, id);
+      uint32_t o = ord_u32(s);
+      bool take = o > vstar;
+      if (!take && o == vstar) {
+        U u = (U)id;
+        if (u < istar) take = true;
+        else if (u == istar) take = atomicAdd(&sm.dup_taken, 1) < ineed;
+      }
+      if (take) {
+        int pos = atomicAdd(&sm.sel_count, 1);
+        if (pos < P) {
+          sel_o[pos] = o;
+          sel_i[pos] = id;
+        }
+      }
+    }
+    __syncthreads();
+    n_sel = min(sm.sel_count, k);
+  }
+
+  if (do_sort) {
+    for (int i = n_sel + tid; i < P; i += nt) {  // padding sorts last
+      sel_o[i] = 0u;
+      sel_i[i] = (IdxT)(~(U)0 >> 1);
+    }
+    for (int size = 2; size <= P; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        __syncthreads();
+        for (int t = tid; t < (P >> 1); t += nt) {
+          int lo = 2 * t - (t & (stride - 1));
+          int hi = lo + stride;
+          bool first_half = (lo & size) == 0;  // ascending ("before" order) in first half of each bitonic block
+          uint32_t oa = sel_o[lo], ob = sel_o[hi];
+          U ia = (U)sel_i[lo], ib = (U)sel_i[hi];
+          bool a_before_b = before<U>(oa, ia, ob, ib);
+          if (a_before_b != first_half) {
+            sel_o[lo] = ob; sel_o[hi] = oa;
+            sel_i[lo] = (IdxT)ib; sel_i[hi] = (IdxT)ia;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  *vstar_out = vstar;
+  return n_sel;
+}
+
+__host__ __device__ inline int pow2ceil(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+// dynamic smem layout: sel_o[P] | sel_i[P]
+template <typename IdxT>
+__global__ void __launch_bounds__(kSelThreads)
+select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __restrict__ cnt, float* __restrict__ tau,
+              int cap, int k, int P, int final_pass, float* __restrict__ out_s, int64_t* __restrict__ out_i,
+              int64_t row_offset) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ SelectSmem<int32_t> sm;
+  int32_t* sel_i = reinterpret_cast<int32_t*>(dyn);
+  uint32_t* sel_o = reinterpret_cast<uint32_t*>(dyn + (size_t)P * sizeof(int32_t));
+  const int q = blockIdx.x;
+  const int n = min(cnt[q], cap);
+  float* ls = cand_s + (size_t)q * cap;
+  int32_t* li = cand_i + (size_t)q * cap;
+  auto load = [&](int i, float& s, int32_t& id) {
+    s = ls[i];
+    id = li[i];
+  };
+  uint32_t vstar;
+  int n_sel = block_select<int32_t>(load, n, k, final_pass != 0, sm, sel_o, sel_i, P, &vstar);
+  __syncthreads();
+  if (final_pass) {
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      if (j < n_sel) {
+        out_s[(size_t)q * k + j] = ord_to_float(sel_o[j]);
+        out_i[(size_t)q * k + j] = (int64_t)sel_i[j] + row_offset;
+      } else {
+        out_s[(size_t)q * k + j] = VODB_NEG_FLT_MAX;
+        out_i[(size_t)q * k + j] = -1;
+      }
+    }
+  } else {
+    if (n > k) {  // compact the survivors to the front of the list
+      for (int j = threadIdx.x; j < n_sel; j += blockDim.x) {
+        ls[j] = ord_to_float(sel_o[j]);
+        li[j] = sel_i[j];
+      }
+      if (threadIdx.x == 0) cnt[q] = n_sel;
+    }
+    if (threadIdx.x == 0) tau[q] = (n >= k) ? ord_to_float(vstar) : -INFINITY;
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, int n_lists, int nq, int k_in,
+             int k_out, int P, float* __restrict__ out_s, int64_t* __restrict__ out_i) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ SelectSmem<int64_t> sm;
+  int64_t* sel_i = reinterpret_cast<int64_t*>(dyn);
+  uint32_t* sel_o = reinterpret_cast<uint32_t*>(dyn + (size_t)P * sizeof(int64_t));
+  const int q = blockIdx.x;
+  const int n = n_lists * k_in;
+  auto load = [&](int i, float& s, int64_t& id) {
+    int l = i / k_in, j = i - l * k_in;
+    size_t off = ((size_t)l * nq + q) * k_in + j;
+    s = scores[off];
+    id = idx[off];
+  };
+  uint32_t vstar;
+  int n_sel = block_select<int64_t>(load, n, k_out, true, sm, sel_o, sel_i, P, &vstar);
+  __syncthreads();
+  for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+    bool ok = j < n_sel && sel_i[j] >= 0;
+    out_s[(size_t)q * k_out + j] = ok ? ord_to_float(sel_o[j]) : VODB_NEG_FLT_MAX;
+    out_i[(size_t)q * k_out + j] = ok ? sel_i[j] : -1;
+  }
+}
+
+__global__ void init_lists_kernel(int* cnt, float* tau, int* overflow, int nq) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) {
+    cnt[i] = 0;
+    tau[i] = -INFINITY;
+  }
+  (void)overflow;  // sticky: cleared by the host after it has been read (vodb_search / vodb_search_check)
+}
+
+}  // namespace
+
+int launch_init_lists(int* cnt, float* tau, int* overflow, int nq, cudaStream_t stream) {
+  init_lists_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(cnt, tau, overflow, nq);
+  VODB_CUDA_CHECK(cudaGetLastError());
+  return VODB_OK;
+}
+
+int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap, int nq, int k, bool final_pass,
+                  float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream) {
+  int P = pow2ceil(k);
+  size_t smem = (size_t)P * (sizeof(int32_t) + sizeof(uint32_t));
+  select_kernel<int32_t><<<nq, kSelThreads, smem, stream>>>(cand_s, cand_i, cnt, tau, cap, k, P, final_pass ? 1 : 0,
+                                                            out_s, out_i, row_offset);
+  VODB_CUDA_CHECK(cudaGetLastError());
+  return VODB_OK;
+}
+
+int launch_merge(const float* scores, const int64_t* idx, int n_lists, int nq, int k_in, int k_out, float* out_s,
+                 int64_t* out_i, cudaStream_t stream) {
+  int P = pow2ceil(k_out);
+  size_t smem = (size_t)P * (sizeof(int64_t) + sizeof(uint32_t));
+  merge_kernel<<<nq, kSelThreads, smem, stream>>>(scores, idx, n_lists, nq, k_in, k_out, P, out_s, out_i);
+  VODB_CUDA_CHECK(cudaGetLastError());
+  return VODB_OK;
+}
+
+}  // namespace vodb
