@@ -123,6 +123,13 @@ int vodb_search_check(vodb_store* s, void* stream);
  * out[4] = max candidates seen in any list, out[5..7] reserved. */
 int vodb_search_stats(const vodb_store* s, int64_t out[8]);
 
+/* Per-kernel timing for bench.py's roofline: while enabled, CUDA events are recorded on the search stream around
+ * every scoring and select launch. vodb_store_profile synchronises the device and returns, summed over the
+ * searches since it was enabled / last read: out[0] = ms in scoring kernels, out[1] = ms in select kernels,
+ * out[2] = number of scoring launches, out[3] = algorithmic corpus bytes those launches scanned (rows*dim*elt). */
+int vodb_store_set_profiling(vodb_store* s, int enable);
+int vodb_store_profile(vodb_store* s, double out[4]);
+
 /* Merge `n_lists` per-shard results. scores: float32 [n_lists, nq, k_in], idx:
  * int64 [n_lists, nq, k_in] (global ids, -1 = empty slot). Writes the k_out best per
  * query in (score desc, id asc) order. All pointers on `device` if on_device. */

@@ -1,0 +1,109 @@
+"""Host-side mirror of the reference interface (no GPU): RetrievalBatch, masters/clients, shard arithmetic."""
+import pickle
+
+import numpy as np
+import pytest
+
+import vod_b200
+from vod_b200 import retrieval as rt
+from vod_b200.search import B200SearchClient, B200SearchMaster, DoNotPickleError, SearchClient
+
+
+def test_retrieval_batch_shape_checks():
+    s, i = np.zeros((2, 3), np.float32), np.zeros((2, 3), np.int64)
+    b = rt.RetrievalBatch(scores=s, indices=i)
+    assert b.shape == (2, 3) and len(b) == 2 and b.labels is None and b.meta == {}
+    with pytest.raises(ValueError):
+        rt.RetrievalBatch(scores=np.zeros((2, 4), np.float32), indices=i)
+    with pytest.raises(ValueError):
+        rt.RetrievalBatch(scores=np.zeros(3, np.float32), indices=np.zeros(3, np.int64))
+    with pytest.raises(ValueError):
+        rt.RetrievalBatch(scores=s, indices=i, labels=np.zeros((2, 2)))
+
+
+def test_retrieval_batch_ops_match_reference_semantics():
+    b = rt.RetrievalBatch.cast(scores=[[1.0, 3.0, 2.0]], indices=[[7, 8, 9]], labels=[[0, 1, 0]])
+    sb = b.sorted()
+    assert sb.scores.tolist() == [[3.0, 2.0, 1.0]] and sb.indices.tolist() == [[8, 9, 7]] and sb.labels.tolist() == [[1, 0, 0]]
+    assert (b * 2.0).scores.tolist() == [[2.0, 6.0, 4.0]]
+    with pytest.raises(TypeError):
+        b * "x"
+    cat = b + b
+    assert cat.shape == (2, 3)
+    sample = b[0]
+    assert isinstance(sample, rt.RetrievalSample) and sample.scores.shape == (3,)
+    stacked = rt.RetrievalBatch.stack_samples([
+        rt.RetrievalSample(scores=np.array([1.0, 2.0]), indices=np.array([4, 5])),
+        rt.RetrievalSample(scores=np.array([3.0]), indices=np.array([6])),
+    ])
+    assert stacked.indices.tolist() == [[4, 5], [6, -1]]
+    assert stacked.scores[1, 1] == -np.inf  # retrieval.py:283-285 padding
+    assert b.to_dict()["indices"] == [[7, 8, 9]]
+    import torch
+
+    c = rt.RetrievalBatch.cast(scores=torch.zeros(1, 2), indices=torch.zeros(1, 2, dtype=torch.int64))
+    assert isinstance(c.scores, np.ndarray)
+
+
+def test_reference_batch_class_is_equivalent_when_available():
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    ref_cls = ref_shim.load()["retrieval"].RetrievalBatch
+    s = np.array([[0.5, 2.0, 1.0], [3.0, -1.0, 0.0]], np.float32)
+    i = np.array([[1, 2, 3], [4, 5, 6]], np.int64)
+    a, b = ref_cls(scores=s, indices=i).sorted(), rt.RetrievalBatch(scores=s, indices=i).sorted()
+    assert np.array_equal(a.scores, b.scores) and np.array_equal(a.indices, b.indices)
+    assert np.array_equal((ref_cls(scores=s, indices=i) * 0.5).scores, (rt.RetrievalBatch(scores=s, indices=i) * 0.5).scores)
+
+
+def test_master_is_unpicklable_and_client_is_a_handle():
+    m = B200SearchMaster(np.zeros((4, 8), np.float32), skip_setup=True)
+    with pytest.raises(DoNotPickleError):
+        pickle.dumps(m)
+    c = m.get_client()
+    assert isinstance(c, SearchClient) and c.requires_vectors is True
+    c2 = pickle.loads(pickle.dumps(c))
+    assert isinstance(c2, B200SearchClient) and c2.master_id == c.master_id
+    assert c2.ping() is False  # master not entered
+    with pytest.raises(vod_b200.VodbError):
+        c2.search(vector=np.zeros((1, 8), np.float32), top_k=3)
+
+
+def test_search_signature_is_keyword_only_like_the_reference():
+    import inspect
+
+    sig = inspect.signature(B200SearchClient.search)
+    for name in ("vector", "text", "subset_ids", "ids", "shard", "top_k"):
+        assert sig.parameters[name].kind is inspect.Parameter.KEYWORD_ONLY
+    assert sig.parameters["top_k"].default == 3
+
+
+def test_shard_bounds_cover_and_align():
+    for n, g in [(10_000_000, 8), (100_000_000, 4), (1000, 2), (130, 8), (0, 2), (128, 1)]:
+        prev = 0
+        for r in range(g):
+            lo, hi = vod_b200.shard_bounds(n, g, r)
+            assert lo == prev and lo <= hi <= n
+            assert lo % 128 == 0 or lo == n
+            prev = hi
+        assert prev == n
+    with pytest.raises(ValueError):
+        vod_b200.shard_bounds(10, 2, 2)
+
+
+def test_sampling_argument_checks_do_not_need_a_gpu():
+    with pytest.raises(ValueError):
+        vod_b200.labeled_priority_sampling(np.zeros((2, 2, 2), np.float32), None)
+    with pytest.raises(ValueError):
+        vod_b200.labeled_priority_sampling(np.zeros((2, 5), np.float32), np.zeros((2, 5), bool), k_positive=4, k_total=2)
+    with pytest.raises(ValueError):
+        vod_b200.priority_sampling_1d(np.zeros((2, 5), np.float32))
+
+
+def test_build_rejects_non_flat_and_matrix_vectors():
+    with pytest.raises(ValueError):
+        vod_b200.build_b200_index(np.zeros((4, 8), np.float32), factory_string="IVF16,Flat")
+    with pytest.raises(ValueError):
+        vod_b200.build_b200_index(np.zeros((4, 8, 2), np.float32))

@@ -1,0 +1,248 @@
+"""Parity of the CUDA search path (through the C ABI) with the IndexFlatIP oracle. Needs a B200."""
+import numpy as np
+import pytest
+
+import vod_b200
+from oracle import flat_ip
+from tests.helpers import int_valued, round_to
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north star: fp32-exact mode, scores within 1e-5 relative, index swaps only between <=1e-5 near-ties
+
+
+def _store(xb, dtype="float32", **kw):
+    st = vod_b200.CorpusStore(len(xb), xb.shape[1], dtype=dtype, **kw)
+    st.add(xb)
+    return st
+
+
+def test_config1_exact_100k_x_768_q256_k100():
+    """BASELINE config 1: faiss IndexFlatIP exact top-100, 100k x 768 fp32, 256 queries."""
+    rng = np.random.default_rng(1234)
+    xb = rng.standard_normal((100_000, 768), dtype=np.float32)
+    xq = rng.standard_normal((256, 768), dtype=np.float32)
+    st = _store(xb)
+    s, i = st.search(xq, 100, mode="exact")
+    rs, ri = flat_ip.search(xb, xq, 100)
+    rep = flat_ip.compare_topk(xb, xq, s, i, rs, ri, rtol=RTOL)
+    assert rep["ok"], rep
+    assert (np.diff(s, axis=1) <= 0).all()
+    assert st.stats()["safe_fallback"] == 0
+    st.close()
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16", "float16"])
+@pytest.mark.parametrize("n,d,nq,k", [(1, 8, 1, 1), (5, 100, 3, 8), (129, 64, 33, 100), (1000, 130, 65, 7),
+                                      (5000, 768, 130, 2048), (40000, 96, 257, 100), (300_000, 64, 9, 10)])
+def test_exact_mode_bit_exact_on_integer_data(dtype, n, d, nq, k):
+    """Integer-valued vectors: every float32 dot product is exact whatever the summation order, so scores, ids,
+    tie-breaking (score desc, id asc) and the -FLT_MAX / -1 padding must match the oracle bit for bit."""
+    rng = np.random.default_rng(n + d)
+    xb, xq = int_valued(rng, (n, d)), int_valued(rng, (nq, d))
+    st = _store(xb, dtype)
+    s, i = st.search(xq, k, mode="exact")
+    rs, ri = flat_ip.search(xb, xq, k)
+    assert np.array_equal(i, ri)
+    assert np.array_equal(s, rs)
+    st.close()
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+@pytest.mark.parametrize("n,d,nq,k", [(1, 8, 1, 1), (130, 64, 5, 100), (1000, 130, 64, 7), (5000, 768, 65, 100),
+                                      (40000, 96, 129, 100), (70000, 768, 300, 1000), (300_000, 64, 9, 10)])
+def test_tensor_mode_bit_exact_on_integer_data(dtype, n, d, nq, k):
+    """Same exactness argument for the tcgen05 path: bf16/fp16 hold small integers exactly, products are exact,
+    fp32 accumulation of integers < 2^24 is exact."""
+    rng = np.random.default_rng(n + d + 1)
+    xb, xq = int_valued(rng, (n, d)), int_valued(rng, (nq, d))
+    st = _store(xb, dtype)
+    s, i = st.search(xq, k, mode="tensor")
+    rs, ri = flat_ip.search(xb, xq, k)
+    assert np.array_equal(i, ri)
+    assert np.array_equal(s, rs)
+    st.close()
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+def test_tensor_mode_recall_and_score_error(dtype):
+    """bf16/fp16 mode: recall@k vs the fp32 oracle on the same stored (rounded) values >= 0.999; score error
+    <= 2e-3 relative (observed ~1e-6: products are exact in fp32, only the accumulation order differs)."""
+    rng = np.random.default_rng(7)
+    xb = round_to(rng.standard_normal((200_000, 768), dtype=np.float32), dtype)
+    xq = round_to(rng.standard_normal((64, 768), dtype=np.float32), dtype)
+    st = _store(xb, dtype)
+    s, i = st.search(xq, 100, mode="tensor")
+    rs, ri = flat_ip.search(xb, xq, 100)
+    assert flat_ip.recall_at_k(i, ri) >= 0.999
+    rep = flat_ip.compare_topk(xb, xq, s, i, rs, ri, rtol=2e-3)
+    assert rep["ok"], rep
+    assert rep["max_score_rel_err"] < 1e-4, rep
+    # exact mode over the same 16-bit store agrees with the oracle at the fp32 tolerance
+    s2, i2 = st.search(xq, 100, mode="exact")
+    rep2 = flat_ip.compare_topk(xb, xq, s2, i2, rs, ri, rtol=RTOL)
+    assert rep2["ok"], rep2
+    st.close()
+
+
+def test_unit_norm_embeddings_stress_near_ties():
+    rng = np.random.default_rng(3)
+    xb = rng.standard_normal((50_000, 256), dtype=np.float32)
+    xb /= np.linalg.norm(xb, axis=1, keepdims=True)
+    xq = rng.standard_normal((40, 256), dtype=np.float32)
+    xq /= np.linalg.norm(xq, axis=1, keepdims=True)
+    st = _store(xb)
+    s, i = st.search(xq, 100, mode="exact")
+    rs, ri = flat_ip.search(xb, xq, 100)
+    rep = flat_ip.compare_topk(xb, xq, s, i, rs, ri, rtol=RTOL)
+    assert rep["ok"], rep
+    st.close()
+
+
+def test_duplicate_rows_and_zero_rows():
+    rng = np.random.default_rng(4)
+    base = int_valued(rng, (50, 32))
+    xb = np.concatenate([base[rng.integers(0, 50, 20000)], np.zeros((3000, 32), np.float32)])
+    xq = int_valued(rng, (17, 32))
+    for dtype, mode in [("float32", "exact"), ("bfloat16", "tensor")]:
+        st = _store(xb, dtype)
+        s, i = st.search(xq, 500, mode=mode)
+        rs, ri = flat_ip.search(xb, xq, 500)
+        assert np.array_equal(i, ri) and np.array_equal(s, rs)
+        st.close()
+
+
+@pytest.mark.parametrize("dtype,mode", [("float32", "exact"), ("bfloat16", "tensor")])
+def test_adversarial_order_triggers_overflow_proof_fallback(dtype, mode):
+    """Rows sorted by increasing score: every row beats the running threshold, lists overflow, the call must fall
+    back to the overflow-proof schedule and still be exact."""
+    n, d = 150_000, 64
+    xb = np.zeros((n, d), np.float32)
+    xb[:, 0] = (np.arange(n) // 64) % 256   # blocks of 64 tied rows, values 0..255 (exact in bf16)
+    xb[:, 1] = np.arange(n) // (64 * 256)   # slow counter 0..9
+    xq = np.zeros((3, d), np.float32)
+    xq[:, 0] = 1.0
+    xq[:, 1] = 256.0                        # score = slow*256 + fast: non-decreasing in the row id
+    st = _store(xb, dtype)
+    s, i = st.search(xq, 100, mode=mode)
+    rs, ri = flat_ip.search(xb, xq, 100)
+    assert np.array_equal(i, ri) and np.array_equal(s, rs)
+    assert st.stats()["safe_fallback"] == 1
+    st.close()
+
+
+def test_host_and_device_entry_points_agree():
+    import torch
+
+    rng = np.random.default_rng(5)
+    xb, xq = int_valued(rng, (30000, 128)), int_valued(rng, (64, 128))
+    st = vod_b200.CorpusStore(len(xb), 128, dtype="bfloat16")
+    st.add(torch.from_numpy(xb).cuda())                       # device-side ingest (build_gpu.py:294-380 analogue)
+    s, i = st.search(xq, 50)
+    ds, di = st.search_device(torch.from_numpy(xq).cuda(), 50)
+    torch.cuda.synchronize()
+    assert not st.check_async()
+    assert np.array_equal(ds.cpu().numpy(), s) and np.array_equal(di.cpu().numpy(), i)
+    dsb, dib = st.search_device(torch.from_numpy(xq).cuda().to(torch.bfloat16), 50, mode="exact")
+    assert np.array_equal(dib.cpu().numpy(), i)
+    st.close()
+
+
+def test_ingest_variants_and_readback():
+    import torch
+
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((1000, 100), dtype=np.float32)
+    for dtype in ("float32", "bfloat16", "float16"):
+        st = vod_b200.CorpusStore(1000, 100, dtype=dtype)
+        st.add(x[:300])
+        st.add(x[300:600].astype(np.float16))                  # fp16 source
+        st.add(torch.from_numpy(x[600:800]).to(torch.bfloat16))  # CPU bf16 tensor
+        st.add(torch.from_numpy(x[800:]).cuda())              # CUDA fp32 tensor
+        assert st.ntotal == 1000
+        got = st.read(0, 1000)
+        exp = np.concatenate([
+            round_to(x[:300], dtype),
+            round_to(x[300:600].astype(np.float16).astype(np.float32), dtype),
+            round_to(round_to(x[600:800], "bfloat16"), dtype),
+            round_to(x[800:], dtype)])
+        assert np.array_equal(got, exp)
+        st.close()
+
+
+def test_synthetic_fill_matches_cpu_twin(twin):
+    for dtype, code in (("float32", 0), ("bfloat16", 1), ("float16", 2)):
+        for unit in (False, True):
+            st = vod_b200.CorpusStore(700, 200, dtype=dtype, row_offset=12345)
+            st.fill_synthetic(99, unit_norm=unit)
+            got = st.read(0, 700)
+            exp = twin.synth_rows(99, 12345, 700, 200, dtype=code, unit_norm=unit)
+            assert np.array_equal(got, exp), (dtype, unit)
+            st.close()
+
+
+def test_row_offset_gives_global_ids_and_merge_matches_unsharded():
+    rng = np.random.default_rng(8)
+    xb, xq = int_valued(rng, (5000, 64)), int_valued(rng, (20, 64))
+    parts = [(0, 2048), (2048, 4096), (4096, 5000)]
+    all_s, all_i = [], []
+    for lo, hi in parts:
+        st = vod_b200.CorpusStore(hi - lo, 64, dtype="float32", row_offset=lo)
+        st.add(xb[lo:hi])
+        s, i = st.search(xq, 300)
+        all_s.append(s)
+        all_i.append(i)
+        st.close()
+    ms, mi = vod_b200.merge_topk(np.stack(all_s), np.stack(all_i), 300)
+    rs, ri = flat_ip.search(xb, xq, 300)
+    assert np.array_equal(mi, ri) and np.array_equal(ms, rs)
+    # a shard smaller than k contributes -1 padded slots that must sort last
+    st = vod_b200.CorpusStore(10, 64, row_offset=7)
+    st.add(xb[:10])
+    s, i = st.search(xq, 300)
+    assert (i[:, 10:] == -1).all() and (i[:, :10] >= 7).all()
+    ms2, mi2 = vod_b200.merge_topk(np.stack([s, s]), np.stack([i, i + np.where(i >= 0, 100, 0)]), 25)
+    assert (mi2[:, 20:] == -1).all() and (ms2[:, 20:] == -np.finfo(np.float32).max).all()
+    st.close()
+
+
+def test_client_master_drop_in():
+    rng = np.random.default_rng(9)
+    vectors = int_valued(rng, (3000, 48))
+    with vod_b200.B200SearchMaster(vectors, dtype="float32") as master:
+        client = master.get_client()
+        assert client.ping()
+        q = int_valued(rng, (10, 48))
+        out = client.search(vector=q, text=["ignored"] * 10, subset_ids=None, ids=None, shard=None, top_k=5)
+        assert type(out).__name__ == "RetrievalBatch"
+        assert out.scores.dtype == np.float32 and out.indices.dtype == np.int64 and out.labels is None
+        assert out.scores.shape == (10, 5) and "time" in out.meta
+        rs, ri = flat_ip.search(vectors, q, 5)
+        assert np.array_equal(out.indices, ri) and np.array_equal(out.scores, rs)
+        out.indices += 100                      # callers mutate results in place (sharded_search.py:103)
+        assert out.scores.flags.writeable
+        with pytest.raises(ValueError):
+            client.search(vector=q[0], top_k=5)  # server.py:82-83
+        with pytest.raises(ValueError):
+            client.search(vector=q[:, :10], top_k=5)
+    assert not client.ping()
+
+
+def test_error_paths():
+    st = vod_b200.CorpusStore(10, 8)
+    with pytest.raises(vod_b200.VodbError):
+        st.search(np.zeros((1, 8), np.float32), 3)        # empty store (server.py:59-62 health check)
+    st.add(np.ones((10, 8), np.float32))
+    with pytest.raises(vod_b200.VodbError):
+        st.search(np.zeros((1, 8), np.float32), 0)
+    with pytest.raises(vod_b200.VodbError):
+        st.search(np.zeros((1, 8), np.float32), 4096)
+    with pytest.raises(vod_b200.VodbError):
+        st.search(np.zeros((1, 8), np.float32), 3, mode="tensor")  # fp32 store has no tensor path
+    with pytest.raises(vod_b200.VodbError):
+        st.add(np.ones((5, 8), np.float32), row0=8)
+    s, i = st.search(np.zeros((0, 8), np.float32), 3)
+    assert s.shape == (0, 3)
+    st.close()
+    with pytest.raises(vod_b200.VodbError):
+        st.search(np.zeros((1, 8), np.float32), 3)

@@ -30,6 +30,27 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_error.c_str(); }
 
+struct ProfileState {
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  // (begin, end, kind) triples; kind 0 = scoring kernel, 1 = select kernel
+  std::vector<int> kinds;
+  double bytes = 0.0;  // algorithmic corpus bytes of the recorded scoring launches
+  cudaEvent_t next() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  void reset() {
+    used = 0;
+    kinds.clear();
+    bytes = 0.0;
+  }
+};
+
 namespace {
 
 struct DeviceGuard {
@@ -313,11 +334,23 @@ int run_scan(vodb_store* s, const void* q_stage, int nq, int k, int mode, bool s
     a.tau = w.tau;
     a.overflow = w.overflow;
     a.cap = w.cap;
+    ProfileState* prof = s->profiling ? static_cast<ProfileState*>(s->prof) : nullptr;
+    if (prof) cudaEventRecord(prof->next(), st);
     rc = (mode == VODB_MODE_TENSOR) ? launch_score_tensor(s, a, st) : launch_score_exact(a, s->sm_count, st);
     if (rc != VODB_OK) return rc;
+    if (prof) {
+      cudaEventRecord(prof->next(), st);
+      prof->kinds.push_back(0);
+      prof->bytes += (double)(b[i + 1] - b[i]) * s->dim * dtype_size(s->dtype);
+      cudaEventRecord(prof->next(), st);
+    }
     bool last = (i + 2 == b.size());
     rc = launch_select(w.cand_s, w.cand_i, w.cnt, w.tau, w.cap, nq, k, last, out_s, out_i, s->row_offset, st);
     if (rc != VODB_OK) return rc;
+    if (prof) {
+      cudaEventRecord(prof->next(), st);
+      prof->kinds.push_back(1);
+    }
     launches += 2;
   }
   s->stats[0] = launches;
@@ -392,6 +425,11 @@ void vodb_store_destroy(vodb_store* s) {
   DeviceGuard guard(s->device);
   cudaDeviceSynchronize();
   free_workspace(s->ws);
+  if (s->prof) {
+    ProfileState* p = static_cast<ProfileState*>(s->prof);
+    for (cudaEvent_t e : p->pool) cudaEventDestroy(e);
+    delete p;
+  }
   if (s->stage) cudaFree(s->stage);
   if (s->data) cudaFree(s->data);
   delete s;
@@ -554,6 +592,36 @@ int vodb_search_check(vodb_store* s, void* stream) {
   VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
   VODB_CUDA_CHECK(cudaStreamSynchronize(st));
   return *w.overflow_host != 0 ? 1 : 0;
+}
+
+int vodb_store_set_profiling(vodb_store* s, int enable) {
+  VODB_REQUIRE(s != nullptr, "vodb_store_set_profiling: store is NULL");
+  if (!s->prof) s->prof = new ProfileState();
+  static_cast<ProfileState*>(s->prof)->reset();
+  s->profiling = enable != 0;
+  return VODB_OK;
+}
+
+int vodb_store_profile(vodb_store* s, double out[4]) {
+  VODB_REQUIRE(s != nullptr && out != nullptr, "vodb_store_profile: NULL argument");
+  out[0] = out[1] = out[2] = out[3] = 0.0;
+  if (!s->prof) return VODB_OK;
+  DeviceGuard guard(s->device);
+  VODB_CUDA_CHECK(cudaDeviceSynchronize());
+  ProfileState* p = static_cast<ProfileState*>(s->prof);
+  for (size_t j = 0; j < p->kinds.size(); ++j) {
+    float ms = 0.f;
+    VODB_CUDA_CHECK(cudaEventElapsedTime(&ms, p->pool[2 * j], p->pool[2 * j + 1]));
+    if (p->kinds[j] == 0) {
+      out[0] += ms;
+      out[2] += 1.0;
+    } else {
+      out[1] += ms;
+    }
+  }
+  out[3] = p->bytes;
+  p->reset();
+  return VODB_OK;
 }
 
 int vodb_search_stats(const vodb_store* s, int64_t out[8]) {

@@ -112,6 +112,9 @@ struct vodb_store {
   alignas(64) unsigned char tmap_corpus[128];
   bool tmap_corpus_valid = false;
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // optional per-kernel timing (vodb_store_set_profiling): events recorded around every scan launch
+  bool profiling = false;
+  void* prof = nullptr;  // vodb::ProfileState*
 };
 
 namespace vodb {

@@ -242,6 +242,15 @@ class CorpusStore:
         _lib.check(rc, "vodb_search_check")
         return rc == 1
 
+    def set_profiling(self, enable: bool) -> None:
+        _lib.check(self._lib.vodb_store_set_profiling(self.handle, int(enable)), "vodb_store_set_profiling")
+
+    def profile(self) -> dict[str, float]:
+        """Summed CUDA-event timings of the scan kernels since profiling was enabled / last read."""
+        arr = (ctypes.c_double * 4)()
+        _lib.check(self._lib.vodb_store_profile(self.handle, arr), "vodb_store_profile")
+        return {"score_ms": arr[0], "select_ms": arr[1], "score_launches": arr[2], "score_bytes": arr[3]}
+
     def stats(self) -> dict[str, int]:
         arr = (ctypes.c_int64 * 8)()
         _lib.check(self._lib.vodb_search_stats(self.handle, arr), "vodb_search_stats")

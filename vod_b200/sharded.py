@@ -61,8 +61,9 @@ class ShardedSearcher:
         B = scores.shape[0]
         all_s = torch.empty((world, B, top_k), dtype=scores.dtype, device=scores.device)
         all_i = torch.empty((world, B, top_k), dtype=ids.dtype, device=ids.device)
-        dist.all_gather_into_tensor(all_s, scores.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(all_i, ids.contiguous(), group=self.group)
+        # concatenated layout [world*B, k]: accepted by both the NCCL and the gloo backend
+        dist.all_gather_into_tensor(all_s.view(world * B, top_k), scores.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(all_i.view(world * B, top_k), ids.contiguous(), group=self.group)
         return self.merge(all_s, all_i, top_k)
 
 
