@@ -1,0 +1,32 @@
+#!/bin/bash
+# Runs on the GPU box through gpurun: smoke, the GPU parity tests (one pytest process per file so that a trapped
+# kernel cannot poison the rest), a short bench, then the ncu passes of B200_PROFILING.md. Logs -> gpurun_out/.
+set -u
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+STEP=${1:-all}
+run() { # name timeout cmd...
+  local name=$1 t=$2; shift 2
+  echo "=== $name" | tee -a gpurun_out/summary.txt
+  timeout "$t" "$@" > "gpurun_out/$name.log" 2>&1
+  echo "exit=$? ($name)" | tee -a gpurun_out/summary.txt
+  tail -n 15 "gpurun_out/$name.log" | tee -a gpurun_out/summary.txt
+}
+: > gpurun_out/summary.txt
+if [[ $STEP == all || $STEP == tests ]]; then
+  run smoke 300 python __graft_entry__.py --smoke
+  run t_search_exact 900 python -m pytest tests/test_search_gpu.py -q -m gpu --timeout=300 -k "exact or config1 or unit_norm or error or ingest or synthetic or client or row_offset" -p no:cacheprovider
+  run t_search_tensor 900 python -m pytest tests/test_search_gpu.py -q -m gpu --timeout=300 -k "tensor or duplicate or adversarial or host_and_device" -p no:cacheprovider
+  run t_sampling 900 python -m pytest tests/test_sampling_gpu.py -q -m gpu --timeout=300 -p no:cacheprovider
+  run t_fullsize 1200 python -m pytest tests/test_fullsize_gpu.py -q -m gpu --timeout=600 -p no:cacheprovider
+fi
+if [[ $STEP == all || $STEP == bench ]]; then
+  run bench 900 python bench.py --steps 20 --warmup 5
+  run bench_ref 600 python bench.py --impl reference --steps 5 --warmup 2
+fi
+if [[ $STEP == all || $STEP == ncu ]]; then
+  run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --large-steps 1
+  run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:score_tc -s 6 -c 3 -o gpurun_out/prof_score_tc python bench.py --steps 2 --warmup 1 --no-cpu --no-large
+fi
+echo "=== done" | tee -a gpurun_out/summary.txt

@@ -382,7 +382,8 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
     s->tmap_corpus_valid = true;
   }
   alignas(64) CUtensorMap tmap_q;
-  int rc = encode_2d(&tmap_q, a.queries, s->dtype, a.nq, s->pitch, BN);
+  // the staged query buffer is zero padded to a multiple of 256 rows (api.cu), so every BN-row box is in bounds
+  int rc = encode_2d(&tmap_q, a.queries, s->dtype, ((int64_t)a.nq + 255) / 256 * 256, s->pitch, BN);
   if (rc != VODB_OK) return rc;
 
   TcParams p;
