@@ -101,7 +101,7 @@ static void spec_log_softmax(float* w, int n, float* scratch) {
     scratch[i] = vodb_expf(w[i]);
   }
   float lse = vodb_logf(spec_sum(scratch, NULL, 0, n));
-  for (int i = 0; i < n; ++i) w[i] = VM_SUB(w[i], lse);
+  for (int i = 0; i < n; ++i) w[i] = vm_canon_nan(VM_SUB(w[i], lse));
 }
 
 static void sample_row(const float* s, const uint8_t* lab, const float* noise, int K, int k_positive,
@@ -163,7 +163,7 @@ static void sample_row(const float* s, const uint8_t* lab, const float* noise, i
     lp[i] = VM_SUB(lp[i], lse[grp[i]]);
     ex[i] = vodb_expf(lp[i]);
   }
-  for (int g = 0; g < 2; ++g) out_lse[g] = vodb_logf(spec_sum(ex, grp, g, K));
+  for (int g = 0; g < 2; ++g) out_lse[g] = vm_canon_nan(vodb_logf(spec_sum(ex, grp, g, K)));
 
   /* keys (sample.py:187-193) and per-group descending order (sample.py:196) */
   for (int i = 0; i < K; ++i) {
@@ -193,7 +193,7 @@ static void sample_row(const float* s, const uint8_t* lab, const float* noise, i
       } else {
         lw = log_pi;
       }
-      w[j] = lw;
+      w[j] = vm_canon_nan(lw);
       out_ids[written + j] = (int64_t)i;
       out_labels[written + j] = (uint8_t)(g == 0);
     }

@@ -190,8 +190,8 @@ sample_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ labe
   __syncthreads();
   block_sum2(ex, grp, K, red, sums);
   if (tid == 0) {
-    out_lse[(size_t)b * 2 + 0] = vodb_logf(sums[0]);
-    out_lse[(size_t)b * 2 + 1] = vodb_logf(sums[1]);
+    out_lse[(size_t)b * 2 + 0] = vm_canon_nan(vodb_logf(sums[0]));
+    out_lse[(size_t)b * 2 + 1] = vm_canon_nan(vodb_logf(sums[1]));
   }
 
   // priority keys (sample.py:187-193) and per-group descending order (sample.py:196)
@@ -230,7 +230,7 @@ sample_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ labe
       } else {
         lw = log_pi;
       }
-      w[j] = lw;
+      w[j] = vm_canon_nan(lw);
       o_ids[written + j] = (int64_t)i;
       o_lab[written + j] = (uint8_t)(g == 0);
     }
@@ -260,7 +260,7 @@ sample_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ labe
       float ws[2];
       block_sum2(scratch, nullptr, n_pick, red, ws);
       float wl = vodb_logf(ws[0]);
-      for (int j = tid; j < n_pick; j += NT) w[j] = VM_SUB(w[j], wl);
+      for (int j = tid; j < n_pick; j += NT) w[j] = vm_canon_nan(VM_SUB(w[j], wl));
       __syncthreads();
     }
     written += n_pick;

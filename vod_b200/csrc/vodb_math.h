@@ -69,6 +69,9 @@ VM_FN float vm_ninf(void) { return vm_u2f(0xff800000u); }
 VM_FN float vm_nan(void) { return vm_u2f(VM_NAN_BITS); }
 VM_FN int vm_isnan(float x) { return (vm_f2u(x) & 0x7fffffffu) > VM_INF_BITS; }
 VM_FN int vm_isinf(float x) { return (vm_f2u(x) & 0x7fffffffu) == VM_INF_BITS; }
+/* NaN sign/payload differs between x86 (default NaN 0xffc00000) and the GPU (0x7fffffff): results that may be
+ * NaN are written through this so that CPU and GPU outputs compare bit for bit. */
+VM_FN float vm_canon_nan(float x) { return vm_isnan(x) ? vm_u2f(VM_NAN_BITS) : x; }
 
 /* natural logarithm */
 VM_FN float vodb_logf(float x) {
