@@ -13,7 +13,7 @@ run() { # name timeout cmd...
   echo "exit=$? ($name)" | tee -a gpurun_out/summary.txt
   tail -n 15 "gpurun_out/$name.log" | tee -a gpurun_out/summary.txt
 }
-: > gpurun_out/summary.txt
+echo "##### $(date) step=$STEP" >> gpurun_out/summary.txt
 if [[ $STEP == all || $STEP == tests ]]; then
   run smoke 300 python __graft_entry__.py --smoke
   run t_search_exact 900 python -m pytest tests/test_search_gpu.py -q -m gpu --timeout=300 -k "exact or config1 or unit_norm or error or ingest or synthetic or client or row_offset" -p no:cacheprovider
@@ -27,6 +27,7 @@ if [[ $STEP == all || $STEP == bench ]]; then
 fi
 if [[ $STEP == all || $STEP == ncu ]]; then
   run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --large-steps 1
-  run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:score_tc -s 6 -c 3 -o gpurun_out/prof_score_tc python bench.py --steps 2 --warmup 1 --no-cpu --no-large
+  run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:score_tc -s 4 -c 4 -o gpurun_out/prof_score_tc python bench.py --steps 2 --warmup 1 --no-cpu --no-large
+  run ncu_full256 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'score_tc_kernel<256>' -s 4 -c 4 -o gpurun_out/prof_score_tc256 python bench.py --steps 1 --warmup 1 --no-cpu --large-steps 1
 fi
 echo "=== done" | tee -a gpurun_out/summary.txt

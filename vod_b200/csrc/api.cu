@@ -315,9 +315,10 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, bool safe) {
 int run_scan(vodb_store* s, const void* q_stage, int nq, int k, int mode, bool safe, float* out_s, int64_t* out_i,
              cudaStream_t st) {
   Workspace& w = s->ws;
-  int rc = launch_init_lists(w.cnt, w.tau, w.overflow, nq, st);
-  if (rc != VODB_OK) return rc;
   std::vector<int64_t> b = plan_segments(s->n_added, w.cap, k, safe);
+  // the first segment (<= cap/2 rows, or <= cap-k in safe mode) stores every score: lists start pre-sized
+  int rc = launch_init_lists(w.cnt, w.tau, (int)(b[1] - b[0]), nq, st);
+  if (rc != VODB_OK) return rc;
   int64_t launches = 1;
   for (size_t i = 0; i + 1 < b.size(); ++i) {
     SegmentArgs a;
@@ -334,6 +335,7 @@ int run_scan(vodb_store* s, const void* q_stage, int nq, int k, int mode, bool s
     a.tau = w.tau;
     a.overflow = w.overflow;
     a.cap = w.cap;
+    a.dump = (i == 0);
     ProfileState* prof = s->profiling ? static_cast<ProfileState*>(s->prof) : nullptr;
     if (prof) cudaEventRecord(prof->next(), st);
     rc = (mode == VODB_MODE_TENSOR) ? launch_score_tensor(s, a, st) : launch_score_exact(a, s->sm_count, st);

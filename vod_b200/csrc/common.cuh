@@ -134,6 +134,7 @@ struct SegmentArgs {
   const float* tau;
   int* overflow;
   int cap;
+  bool dump;            // first segment of a scan: lists are empty, every score is stored at slot row-row_begin
 };
 
 int launch_score_exact(const SegmentArgs& a, int sm_count, cudaStream_t stream);
@@ -145,7 +146,7 @@ int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap,
                   float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream);
 int launch_merge(const float* scores, const int64_t* idx, int n_lists, int nq, int k_in, int k_out, float* out_s,
                  int64_t* out_i, cudaStream_t stream);
-int launch_init_lists(int* cnt, float* tau, int* overflow, int nq, cudaStream_t stream);
+int launch_init_lists(int* cnt, float* tau, int first_rows, int nq, cudaStream_t stream);
 
 int launch_convert_rows(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch,
                         int64_t n, cudaStream_t stream);

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kThreads)
 score_exact_kernel(const T* __restrict__ corpus, int pitch, int64_t row_begin, int64_t row_end,
                    const float* __restrict__ queries, int nq, float* __restrict__ cand_s,
                    int32_t* __restrict__ cand_i, int* __restrict__ cnt, const float* __restrict__ tau,
-                   int* __restrict__ overflow, int cap) {
+                   int* __restrict__ overflow, int cap, int dump) {
   constexpr int TN = BN / 16;
   constexpr int A_LOADS = BM * BK / 4 / kThreads;                      // vec4 loads per thread (=4)
   constexpr int B_LOADS = (BN * BK / 4 + kThreads - 1) / kThreads;     // 4 / 2 / 1
@@ -163,7 +163,12 @@ score_exact_kernel(const T* __restrict__ corpus, int pitch, int64_t row_begin, i
       else n = tx * TN + j;
       int q = q0 + n;
       float s = acc[i][j];
-      if (q < nq && s >= tau_s[n]) {
+      if (dump) {  // first segment: every score is a candidate, slot = row - row_begin (no atomics)
+        if (q < nq) {
+          cand_s[(size_t)q * cap + (size_t)(r - row_begin)] = s;
+          cand_i[(size_t)q * cap + (size_t)(r - row_begin)] = (int32_t)r;
+        }
+      } else if (q < nq && s >= tau_s[n]) {
         int pos = atomicAdd(&cnt[q], 1);
         if (pos < cap) {
           cand_s[(size_t)q * cap + pos] = s;
@@ -187,15 +192,15 @@ int launch_typed(const SegmentArgs& a, cudaStream_t stream) {
   if (a.nq > 64) {
     dim3 grid((unsigned)tiles, (a.nq + 127) / 128);
     score_exact_kernel<T, 128><<<grid, kThreads, 0, stream>>>(corpus, a.pitch, a.row_begin, a.row_end, q, a.nq,
-                                                              a.cand_s, a.cand_i, a.cnt, a.tau, a.overflow, a.cap);
+                                                              a.cand_s, a.cand_i, a.cnt, a.tau, a.overflow, a.cap, a.dump ? 1 : 0);
   } else if (a.nq > 32) {
     dim3 grid((unsigned)tiles, 1);
     score_exact_kernel<T, 64><<<grid, kThreads, 0, stream>>>(corpus, a.pitch, a.row_begin, a.row_end, q, a.nq,
-                                                             a.cand_s, a.cand_i, a.cnt, a.tau, a.overflow, a.cap);
+                                                             a.cand_s, a.cand_i, a.cnt, a.tau, a.overflow, a.cap, a.dump ? 1 : 0);
   } else {
     dim3 grid((unsigned)tiles, 1);
     score_exact_kernel<T, 32><<<grid, kThreads, 0, stream>>>(corpus, a.pitch, a.row_begin, a.row_end, q, a.nq,
-                                                             a.cand_s, a.cand_i, a.cnt, a.tau, a.overflow, a.cap);
+                                                             a.cand_s, a.cand_i, a.cnt, a.tau, a.overflow, a.cap, a.dump ? 1 : 0);
   }
   VODB_CUDA_CHECK(cudaGetLastError());
   return VODB_OK;

@@ -141,7 +141,62 @@ struct TcParams {
   int* overflow;
   int cap;
   uint32_t idesc;
+  int dump;  // first segment: store every score at slot (row - row_begin) instead of filtering
 };
+
+// CTA-level staging of filter survivors (shared memory): pushed with shared-memory atomics by the epilogue
+// threads, appended to the global per-query lists in bulk so that the L2 atomic latency (~0.7 us) is paid once
+// per batch of entries instead of once per surviving score.
+constexpr int kStageCap = 512;
+struct StageBuf {
+  int count[2];
+  int pad[2];
+  float s[2][kStageCap];
+  int32_t row[2][kStageCap];
+  int32_t q[2][kStageCap];
+};
+
+__device__ __forceinline__ void append_global(const TcParams& p, int q, float s, int32_t row) {
+  const int pos = atomicAdd(&p.cnt[q], 1);
+  if (pos < p.cap) {
+    p.cand_s[(size_t)q * p.cap + pos] = s;
+    p.cand_i[(size_t)q * p.cap + pos] = row;
+  } else {
+    *p.overflow = 1;
+  }
+}
+
+// 128 epilogue threads append the staged entries of buffer `b` to the global lists; up to 4 atomics in flight per thread
+__device__ __forceinline__ void flush_staged(const TcParams& p, StageBuf& stg, int b, int et) {
+  const int n = min(stg.count[b], kStageCap);
+  if (n == 0) return;
+  constexpr int U = kStageCap / 128;
+  float fs[U];
+  int32_t fr[U], fq[U];
+  int pos[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int e = et + u * 128;
+    pos[u] = -1;
+    if (e < n) {
+      fs[u] = stg.s[b][e];
+      fr[u] = stg.row[b][e];
+      fq[u] = stg.q[b][e];
+      pos[u] = atomicAdd(&p.cnt[fq[u]], 1);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (pos[u] >= 0) {
+      if (pos[u] < p.cap) {
+        p.cand_s[(size_t)fq[u] * p.cap + pos[u]] = fs[u];
+        p.cand_i[(size_t)fq[u] * p.cap + pos[u]] = fr[u];
+      } else {
+        *p.overflow = 1;
+      }
+    }
+  }
+}
 
 template <int BN>
 struct TcConfig {
@@ -152,7 +207,7 @@ struct TcConfig {
   static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                         : (2 * BN <= 256) ? 256 : 512;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                         2 * BN * sizeof(float) /*tau*/;
+                                         2 * BN * sizeof(float) /*tau*/ + sizeof(StageBuf);
 };
 
 template <int BN>
@@ -173,6 +228,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* tau_s = reinterpret_cast<float*>(bars + 2 * STAGES + 6);  // [2][BN]
+  StageBuf& stg = *reinterpret_cast<StageBuf*>(tau_s + 2 * BN);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -186,6 +242,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 4);
     }
+    stg.count[0] = 0;
+    stg.count[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -260,10 +318,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int q0 = qt * BN;
+      const int sb = local & 1;  // staging buffer that receives this item's survivors
       float* tau_cur = tau_s + acc * BN;
-      // stage this query tile's thresholds (queries past nq never pass)
-      for (int c = et; c < BN; c += 128) tau_cur[c] = (q0 + c < p.nq) ? p.tau[q0 + c] : INFINITY;
+      // (A) every epilogue thread has finished pushing the previous item's survivors
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (!p.dump) {
+        if (local > 0) flush_staged(p, stg, sb ^ 1, et);
+        // stage this query tile's thresholds (queries past nq never pass)
+        for (int c = et; c < BN; c += 128) tau_cur[c] = (q0 + c < p.nq) ? p.tau[q0 + c] : INFINITY;
+      }
+      // (B) everybody has read the flushed buffer's count; its counter may be reset (next pushed to after the next (A))
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) stg.count[sb ^ 1] = 0;
 
       const int64_t row = p.row_begin + (int64_t)ct * BM + quarter * 32 + lane;
       const bool valid = row < p.row_end;
@@ -276,6 +342,21 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr0 + (uint32_t)c0, v);
         tmem_ld_wait();
+        if (p.dump) {
+          // first segment: every score is a candidate; slot = row - row_begin, no atomics, coalesced over lanes
+          if (valid) {
+            const size_t slot = (size_t)(row - p.row_begin);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int q = q0 + c0 + j;
+              if (q < p.nq) {
+                p.cand_s[(size_t)q * p.cap + slot] = __uint_as_float(v[j]);
+                p.cand_i[(size_t)q * p.cap + slot] = (int32_t)row;
+              }
+            }
+          }
+          continue;
+        }
         bool any = false;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -284,25 +365,22 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
                  (__uint_as_float(v[j4 * 4 + 2]) >= t.z) | (__uint_as_float(v[j4 * 4 + 3]) >= t.w);
         }
         any = any && valid;
-        if (__any_sync(0xffffffffu, any)) {
+        {
+          if (any) {
+            // rare: push survivors into the CTA's shared staging buffer (shared-memory atomics only); the global
+            // list append (one L2 atomic round trip per entry) is done in bulk by flush_staged, 128 threads wide
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s = __uint_as_float(v[j]);
-            const bool pass = valid && (s >= tau_cur[c0 + j]);
-            const unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (m != 0u) {
-              const int q = q0 + c0 + j;
-              const int leader = __ffs(m) - 1;
-              int base = 0;
-              if (lane == leader) base = atomicAdd(&p.cnt[q], __popc(m));
-              base = __shfl_sync(0xffffffffu, base, leader);
-              if (pass) {
-                const int pos = base + __popc(m & ((1u << lane) - 1u));
-                if (pos < p.cap) {
-                  p.cand_s[(size_t)q * p.cap + pos] = s;
-                  p.cand_i[(size_t)q * p.cap + pos] = (int32_t)row;
+            for (int j = 0; j < 32; ++j) {
+              const float s = __uint_as_float(v[j]);
+              if (s >= tau_cur[c0 + j]) {
+                const int q = q0 + c0 + j;
+                const int idx = atomicAdd(&stg.count[sb], 1);
+                if (idx < kStageCap) {
+                  stg.s[sb][idx] = s;
+                  stg.row[sb][idx] = (int32_t)row;
+                  stg.q[sb][idx] = q;
                 } else {
-                  *p.overflow = 1;
+                  append_global(p, q, s, (int32_t)row);  // staging full: slow but correct
                 }
               }
             }
@@ -314,6 +392,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (!p.dump && local > 0) flush_staged(p, stg, (local - 1) & 1, et);
   }
 
   tcgen05_fence_before();
@@ -399,6 +479,7 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.tau = a.tau;
   p.overflow = a.overflow;
   p.cap = a.cap;
+  p.dump = a.dump ? 1 : 0;
   const uint32_t fmt = (s->dtype == VODB_BF16) ? 1u : 0u;  // UMMA F16F32Format: F16=0, BF16=1
   p.idesc = (1u << 4) /*D=f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;

@@ -44,6 +44,43 @@ __device__ __forceinline__ bool before(uint32_t oa, U ia, uint32_t ob, U ib) {
   return (oa > ob) || (oa == ob && ia < ib);
 }
 
+// One warp locates the histogram bin holding the `need`-th entry, scanning bins from the top (kDescending) or the
+// bottom: lane l owns 8 consecutive bins in scan order, a warp prefix sum over the lane totals finds the lane, the
+// lane walks its 8 bins. Writes sm.bin, sm.need (rank inside the bin, 1-based) and sm.n_eq (size of the bin).
+template <bool kDescending, typename IdxT>
+__device__ __forceinline__ void find_bin(SelectSmem<IdxT>& sm, int need, int lane) {
+  int h[8];
+  int total = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int pos = lane * 8 + j;  // position in scan order
+    const int bin = kDescending ? 255 - pos : pos;
+    h[j] = sm.hist[bin];
+    total += h[j];
+  }
+  int incl = total;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  const int excl = incl - total;
+  // the first lane whose inclusive count reaches `need` owns the bin (the last lane takes it if none does)
+  const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
+  const int owner = hit ? (__ffs(hit) - 1) : 31;
+  if (lane == owner) {
+    int cum = excl, j = 0;
+    for (; j < 7; ++j) {
+      if (cum + h[j] >= need) break;
+      cum += h[j];
+    }
+    const int pos = lane * 8 + j;
+    sm.bin = kDescending ? 255 - pos : pos;
+    sm.need = need - cum;
+    sm.n_eq = h[j];
+  }
+}
+
 // Core routine. load(i, score, idx) reads entry i in [0,n). Results: sel_o/sel_i[0..n_sel) in shared
 // memory (sorted if do_sort), returns n_sel = min(n,k); *vstar_out = ord image of the k-th best score
 // (0 if n < k).
@@ -87,17 +124,7 @@ __device__ int block_select(Loader load, int n, int k, bool do_sort, SelectSmem<
         if ((o & mask) == prefix) atomicAdd(&sm.hist[(o >> shift) & 255u], 1);
       }
       __syncthreads();
-      if (tid == 0) {
-        int cum = 0, b = 255;
-        for (; b > 0; --b) {
-          int h = sm.hist[b];
-          if (cum + h >= need) break;
-          cum += h;
-        }
-        sm.bin = b;
-        sm.need = need - cum;
-        sm.n_eq = sm.hist[b];
-      }
+      if (tid < 32) find_bin<true>(sm, need, tid);
       __syncthreads();
       prefix |= (uint32_t)sm.bin << shift;
       mask |= 0xffu << shift;
@@ -122,16 +149,7 @@ __device__ int block_select(Loader load, int n, int k, bool do_sort, SelectSmem<
           if (ord_u32(s) == vstar && (((U)id) & imask) == iprefix) atomicAdd(&sm.hist[(int)((((U)id) >> shift) & 255u)], 1);
         }
         __syncthreads();
-        if (tid == 0) {
-          int cum = 0, b = 0;
-          for (; b < 255; ++b) {
-            int h = sm.hist[b];
-            if (cum + h >= ineed) break;
-            cum += h;
-          }
-          sm.bin = b;
-          sm.need = ineed - cum;
-        }
+        if (tid < 32) find_bin<false>(sm, ineed, tid);
         __syncthreads();
         iprefix |= (U)sm.bin << shift;
         imask |= (U)0xff << shift;
@@ -270,19 +288,21 @@ merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, 
   }
 }
 
-__global__ void init_lists_kernel(int* cnt, float* tau, int* overflow, int nq) {
+// cnt starts at the row count of the first scan segment: that segment stores every score at slot row-row_begin
+// ("dump" mode of the scoring kernels), so the lists are pre-sized instead of grown with atomics.
+// The overflow flag is sticky: cleared by the host after it has been read (vodb_search / vodb_search_check).
+__global__ void init_lists_kernel(int* cnt, float* tau, int first_rows, int nq) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nq) {
-    cnt[i] = 0;
+    cnt[i] = first_rows;
     tau[i] = -INFINITY;
   }
-  (void)overflow;  // sticky: cleared by the host after it has been read (vodb_search / vodb_search_check)
 }
 
 }  // namespace
 
-int launch_init_lists(int* cnt, float* tau, int* overflow, int nq, cudaStream_t stream) {
-  init_lists_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(cnt, tau, overflow, nq);
+int launch_init_lists(int* cnt, float* tau, int first_rows, int nq, cudaStream_t stream) {
+  init_lists_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(cnt, tau, first_rows, nq);
   VODB_CUDA_CHECK(cudaGetLastError());
   return VODB_OK;
 }
