@@ -166,34 +166,44 @@ __device__ __forceinline__ void append_global(const TcParams& p, int q, float s,
   }
 }
 
-// 128 epilogue threads append the staged entries of buffer `b` to the global lists; up to 4 atomics in flight per thread
-__device__ __forceinline__ void flush_staged(const TcParams& p, StageBuf& stg, int b, int et) {
+// Bulk append of the staged entries of buffer `b` to the global lists by the 128 epilogue threads, split in two
+// halves so that the L2 atomic round trip (several microseconds when the L2 is saturated by the operand stream)
+// overlaps the next item's epilogue work: `issue` copies the entries to registers and fires the slot-reserving
+// atomics, `complete` (called after the item's score columns have been processed) consumes the slots.
+constexpr int kFlushPerThread = kStageCap / 128;
+struct PendingFlush {
+  float s[kFlushPerThread];
+  int32_t row[kFlushPerThread];
+  int32_t q[kFlushPerThread];
+  int pos[kFlushPerThread];
+};
+
+__device__ __forceinline__ void flush_issue(const TcParams& p, const StageBuf& stg, int b, int et, PendingFlush& f) {
   const int n = min(stg.count[b], kStageCap);
-  if (n == 0) return;
-  constexpr int U = kStageCap / 128;
-  float fs[U];
-  int32_t fr[U], fq[U];
-  int pos[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
+  for (int u = 0; u < kFlushPerThread; ++u) {
     const int e = et + u * 128;
-    pos[u] = -1;
+    f.pos[u] = -1;
     if (e < n) {
-      fs[u] = stg.s[b][e];
-      fr[u] = stg.row[b][e];
-      fq[u] = stg.q[b][e];
-      pos[u] = atomicAdd(&p.cnt[fq[u]], 1);
+      f.s[u] = stg.s[b][e];
+      f.row[u] = stg.row[b][e];
+      f.q[u] = stg.q[b][e];
+      f.pos[u] = atomicAdd(&p.cnt[f.q[u]], 1);
     }
   }
+}
+
+__device__ __forceinline__ void flush_complete(const TcParams& p, PendingFlush& f) {
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    if (pos[u] >= 0) {
-      if (pos[u] < p.cap) {
-        p.cand_s[(size_t)fq[u] * p.cap + pos[u]] = fs[u];
-        p.cand_i[(size_t)fq[u] * p.cap + pos[u]] = fr[u];
+  for (int u = 0; u < kFlushPerThread; ++u) {
+    if (f.pos[u] >= 0) {
+      if (f.pos[u] < p.cap) {
+        p.cand_s[(size_t)f.q[u] * p.cap + f.pos[u]] = f.s[u];
+        p.cand_i[(size_t)f.q[u] * p.cap + f.pos[u]] = f.row[u];
       } else {
         *p.overflow = 1;
       }
+      f.pos[u] = -1;
     }
   }
 }
@@ -313,6 +323,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int et = threadIdx.x - 64;  // 0..127
     int local = 0;
+    PendingFlush pend;
+#pragma unroll
+    for (int u = 0; u < kFlushPerThread; ++u) pend.pos[u] = -1;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
       const int ct = item / p.n_qtiles, qt = item - ct * p.n_qtiles;
       const int acc = local & 1;
@@ -323,7 +336,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       // (A) every epilogue thread has finished pushing the previous item's survivors
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (!p.dump) {
-        if (local > 0) flush_staged(p, stg, sb ^ 1, et);
+        if (local > 0) flush_issue(p, stg, sb ^ 1, et, pend);
         // stage this query tile's thresholds (queries past nq never pass)
         for (int c = et; c < BN; c += 128) tau_cur[c] = (q0 + c < p.nq) ? p.tau[q0 + c] : INFINITY;
       }
@@ -391,9 +404,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      flush_complete(p, pend);  // slots reserved at the top of this item have arrived by now
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (!p.dump && local > 0) flush_staged(p, stg, (local - 1) & 1, et);
+    if (!p.dump && local > 0) {
+      flush_issue(p, stg, (local - 1) & 1, et, pend);
+      flush_complete(p, pend);
+    }
   }
 
   tcgen05_fence_before();
