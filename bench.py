@@ -50,6 +50,7 @@ def parse_args():
     p.add_argument("--no-large", action="store_true", help="skip the 8192-query section")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     p.add_argument("--large-steps", type=int, default=3)
+    p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="cross-shard exchange (N>1)")
     return p.parse_args()
 
 
@@ -167,7 +168,10 @@ def workload_config(args, mode):
     return {
         "workload": f"BASELINE configs[1]: exact MIPS top-{TOP_K}, {args.rows} x {DIM} bf16 corpus, {Q_SMALL}-query batches",
         "rows": args.rows, "dim": DIM, "store_dtype": "bf16", "queries_per_batch": Q_SMALL, "top_k": TOP_K,
-        "mode": mode, "sharding": f"rows split over {args.gpus} rank(s), all-gather + merge" if args.gpus > 1 else "single shard",
+        "mode": mode,
+        "sharding": (f"rows split over {args.gpus} ranks; exchange={getattr(args, 'exchange', 'p2p')} "
+                     "(p2p = final select stores into peer-mapped buffers + flag, merge kernel waits; nccl = all-gather + merge)")
+        if args.gpus > 1 else "single shard",
         "l2": "inputs larger than L2: the corpus shard streamed every step is >= 1.9 GB (L2 = 126 MB); fresh queries per step",
     }
 
@@ -207,7 +211,8 @@ def main():
         return float(t.item())
 
     # ---- corpus: row shard of the global synthetic corpus, generated on the device ----
-    corpus = vod_b200.ShardedCorpus(args.rows, DIM, dtype="bfloat16", device=local_rank, rank=rank, world_size=world)
+    corpus = vod_b200.ShardedCorpus(args.rows, DIM, dtype="bfloat16", device=local_rank, rank=rank, world_size=world,
+                                    exchange=args.exchange, max_queries=Q_LARGE, max_k=TOP_K)
     corpus.fill_synthetic(CORPUS_SEED)
     torch.cuda.synchronize()
     shard_rows = corpus.hi - corpus.lo
@@ -218,7 +223,7 @@ def main():
         for i in range(warmup):
             corpus.search_device(queries[i], TOP_K, mode="tensor")
         torch.cuda.synchronize()
-        assert not corpus.store.check_async(), "candidate list overflow during warm-up"
+        assert not corpus.any_overflow(), "candidate list overflow during warm-up"
         sampler = ClockSampler(local_rank) if sample_clocks else None
         if sampler:
             sampler.start()
@@ -232,7 +237,7 @@ def main():
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
         clocks = sampler.stop() if sampler else None
-        assert not corpus.store.check_async(), "candidate list overflow in the timed region (results invalid)"
+        assert not corpus.any_overflow(), "candidate list overflow in the timed region (results invalid)"
         stats = corpus.store.stats()
         # kernel-only time of the scoring kernel: CUDA events around every launch, separate pass over the same workload
         corpus.store.set_profiling(True)
@@ -247,6 +252,7 @@ def main():
     score_ms_per_search = max_over_ranks(prof["score_ms"] / args.steps)
     achieved_gbs = shard_bytes / (score_ms_per_search * 1e-3) / 1e9
     # kernels per search on this rank: convert queries + init lists + (score, select) per segment (+ merge)
+    # (with N>1 the merge kernel is one more launch; the p2p exchange itself adds none, NCCL adds two collectives)
     launches_per_step = 1 + int(stats["launches"]) + (1 if world > 1 else 0)
     roofline = {
         "bound": "hbm", "kernel": "score_tc_kernel<64> (tcgen05 + TMA, fused top-k filter)",

@@ -137,6 +137,27 @@ int vodb_merge_topk(int device, const float* scores, const int64_t* idx, int n_l
                     int k_in, int k_out, float* out_scores, int64_t* out_idx, int on_device,
                     void* stream);
 
+/* ---- cross-shard exchange fused into the search (one process per GPU, peer-mapped buffers over NVLink) ------
+ *
+ * Replaces faiss' IndexShards host-side merge (index_cpu_to_all_gpus with co.shard=True, server.py:51-54) and the
+ * NCCL all-gather of the unfused path: the final select kernel of every rank stores its [nq,k] (score, global id)
+ * list directly into every peer's gather buffer and publishes an epoch flag; the merge kernel waits on its own
+ * flags and reduces world*k -> k. Set-up: every rank calls vodb_xchg_create, the 64-byte handles are all-gathered
+ * by the host code (torch.distributed), then every rank calls vodb_xchg_connect with the world*64 handle bytes
+ * (rank-major). All ranks must then call vodb_search_sharded the same number of times, in the same order. */
+#define VODB_IPC_HANDLE_BYTES 64
+typedef struct vodb_xchg vodb_xchg;
+int vodb_xchg_create(vodb_xchg** out, int device, int rank, int world, int max_nq, int max_k,
+                     unsigned char* handle_out /* VODB_IPC_HANDLE_BYTES */);
+int vodb_xchg_connect(vodb_xchg* x, const unsigned char* all_handles /* world * VODB_IPC_HANDLE_BYTES */);
+void vodb_xchg_destroy(vodb_xchg* x);
+/* Like vodb_search over this rank's shard, but out_scores / out_idx receive the MERGED result of all shards (every
+ * rank gets the same [nq,k] arrays). `safe` != 0 selects the overflow-proof scan schedule (all ranks must pass the
+ * same value): callers that saw vodb_search_check()==1 on ANY rank re-run the batch with safe=1 on ALL ranks. */
+int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_dtype, int q_on_device, int nq,
+                        int k, int mode, int safe, float* out_scores, int64_t* out_idx, int out_on_device,
+                        void* stream);
+
 /* ---- labeled priority sampling ------------------------------------------ */
 
 /* Per row b of scores[B,K]: split entries by labels[b,:] > 0, priority-sample

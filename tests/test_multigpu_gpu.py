@@ -1,0 +1,76 @@
+"""Row-sharded search on >= 2 GPUs of one box (skipped on single-GPU boxes): the fused peer-memory exchange and the
+NCCL all-gather path must both reproduce the single-shard result bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank: int, world: int, port: int, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    ok, msg = True, ""
+    try:
+        import vod_b200
+
+        n, d, k = 1_000_003, 256, 100
+        g = torch.Generator().manual_seed(5)
+        xq = torch.randn((64, d), generator=g).to(torch.bfloat16).to(torch.float32)
+        results = {}
+        for exchange in ("p2p", "nccl"):
+            corpus = vod_b200.ShardedCorpus(n, d, dtype="bfloat16", device=rank, rank=rank, world_size=world,
+                                            exchange=exchange, max_queries=256, max_k=1000)
+            corpus.fill_synthetic(77)
+            for rep in range(3):  # several epochs: exercises the parity double-buffering of the exchange
+                s, i = corpus.search_device(xq.cuda(), k, mode="tensor")
+            s2, i2 = corpus.search_device(xq[:7].cuda(), 1000, mode="exact")
+            torch.cuda.synchronize()
+            assert not corpus.any_overflow()
+            results[exchange] = (s.cpu().numpy(), i.cpu().numpy(), s2.cpu().numpy(), i2.cpu().numpy())
+            corpus.close()
+        a, b = results["p2p"], results["nccl"]
+        for x, y in zip(a, b):
+            if not np.array_equal(x, y):
+                ok, msg = False, "p2p and nccl exchange disagree"
+        if rank == 0 and ok:
+            single = vod_b200.CorpusStore(n, d, dtype="bfloat16", device=0)
+            single.fill_synthetic(77)
+            ss, si = single.search(xq.numpy(), k, mode="tensor")
+            ss2, si2 = single.search(xq[:7].numpy(), 1000, mode="exact")
+            single.close()
+            if not (np.array_equal(si, a[1]) and np.array_equal(ss, a[0])):
+                ok, msg = False, "sharded tensor-mode result differs from the single-shard result"
+            if not (np.array_equal(si2, a[3]) and np.array_equal(ss2, a[2])):
+                ok, msg = False, "sharded exact-mode result differs from the single-shard result"
+        dist.barrier()
+    except Exception as exc:  # report instead of hanging the other rank
+        ok, msg = False, f"{type(exc).__name__}: {exc}"
+    q.put((rank, ok, msg))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_search_two_gpus():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(torch.cuda.device_count(), 4)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=500) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in results), results

@@ -49,6 +49,11 @@ _SIGNATURES = {
     "vodb_search_stats": (_c.c_int, [_vp, _c.POINTER(_c.c_int64)]),
     "vodb_store_set_profiling": (_c.c_int, [_vp, _c.c_int]),
     "vodb_store_profile": (_c.c_int, [_vp, _c.POINTER(_c.c_double)]),
+    "vodb_xchg_create": (_c.c_int, [_c.POINTER(_vp), _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _vp]),
+    "vodb_xchg_connect": (_c.c_int, [_vp, _vp]),
+    "vodb_xchg_destroy": (None, [_vp]),
+    "vodb_search_sharded": (_c.c_int, [_vp, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _vp,
+                                       _vp, _c.c_int, _vp]),
     "vodb_merge_topk": (_c.c_int, [_c.c_int, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _vp, _vp, _c.c_int, _vp]),
     "vodb_sample": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float,
                                _c.c_int, _c.c_int, _c.c_uint64, _c.c_uint64, _vp, _vp, _vp, _vp, _c.c_int, _vp]),

@@ -313,7 +313,7 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, bool safe) {
 }
 
 int run_scan(vodb_store* s, const void* q_stage, int nq, int k, int mode, bool safe, float* out_s, int64_t* out_i,
-             cudaStream_t st) {
+             cudaStream_t st, const ExchangeDst* xd = nullptr) {
   Workspace& w = s->ws;
   std::vector<int64_t> b = plan_segments(s->n_added, w.cap, k, safe);
   // the first segment (<= cap/2 rows, or <= cap-k in safe mode) stores every score: lists start pre-sized
@@ -347,7 +347,8 @@ int run_scan(vodb_store* s, const void* q_stage, int nq, int k, int mode, bool s
       cudaEventRecord(prof->next(), st);
     }
     bool last = (i + 2 == b.size());
-    rc = launch_select(w.cand_s, w.cand_i, w.cnt, w.tau, w.cap, nq, k, last, out_s, out_i, s->row_offset, st);
+    rc = launch_select(w.cand_s, w.cand_i, w.cnt, w.tau, w.cap, nq, k, last, out_s, out_i, s->row_offset, st,
+                       last ? xd : nullptr);
     if (rc != VODB_OK) return rc;
     if (prof) {
       cudaEventRecord(prof->next(), st);
@@ -367,6 +368,51 @@ int run_scan(vodb_store* s, const void* q_stage, int nq, int k, int mode, bool s
 }  // namespace vodb
 
 using namespace vodb;
+
+// Peer-mapped exchange buffers of one rank (vodb_xchg_*): [flags 2 x kMaxPeers u32 | pad to 256 B |
+// gather scores 2 x world x slot f32 | gather ids 2 x world x slot i64], exported to the peers through CUDA IPC.
+struct vodb_xchg {
+  int device = 0, rank = 0, world = 1;
+  int max_nq = 0, max_k = 0;
+  size_t slot = 0;            // elements per (parity, source rank) slot = max_nq * max_k
+  size_t bytes = 0;
+  char* local = nullptr;      // this rank's buffer
+  char* peer[kMaxPeers] = {}; // peer-mapped base pointers (peer[rank] == local)
+  bool connected = false;
+  int* done_counter = nullptr;
+  uint32_t epoch = 0;
+  static size_t off_flags() { return 0; }
+  static size_t off_s() { return 256; }
+  size_t off_i() const { return off_s() + (((size_t)2 * world * slot * sizeof(float)) + 255) / 256 * 256; }
+};
+
+namespace {
+// convert / pad the query batch into the store's staging buffer (shared by vodb_search and vodb_search_sharded)
+int stage_queries(vodb_store* s, const void* queries, int q_dtype, int q_on_device, int nq, int mode, cudaStream_t st) {
+  Workspace& w = s->ws;
+  const void* q_dev = queries;
+  if (!q_on_device) {
+    VODB_CUDA_CHECK(cudaMemcpyAsync(w.q_in, queries, (size_t)nq * s->dim * dtype_size(q_dtype), cudaMemcpyHostToDevice, st));
+    q_dev = w.q_in;
+  }
+  const int stage_dtype = (mode == VODB_MODE_TENSOR) ? s->dtype : VODB_F32;
+  size_t rows_pad = ((size_t)nq + 255) / 256 * 256;
+  VODB_CUDA_CHECK(cudaMemsetAsync(w.q_stage, 0, rows_pad * s->pitch * dtype_size(stage_dtype), st));
+  return launch_convert_rows(q_dev, q_dtype, s->dim, w.q_stage, stage_dtype, s->pitch, nq, st);
+}
+
+int check_search_args(vodb_store* s, const void* queries, int q_dtype, int nq, int k, int mode, const float* out_scores,
+                      const int64_t* out_idx, const char* fn) {
+  VODB_REQUIRE(s != nullptr, "%s: store is NULL", fn);
+  VODB_REQUIRE(queries != nullptr || nq == 0, "%s: queries is NULL", fn);
+  VODB_REQUIRE(nq >= 0, "%s: nq=%d < 0", fn, nq);
+  VODB_REQUIRE(k >= 1 && k <= VODB_MAX_K, "%s: k=%d outside [1, %d]", fn, k, VODB_MAX_K);
+  VODB_REQUIRE(q_dtype == VODB_F32 || q_dtype == VODB_BF16 || q_dtype == VODB_F16, "%s: bad query dtype %d", fn, q_dtype);
+  VODB_REQUIRE(mode == VODB_MODE_EXACT || mode == VODB_MODE_TENSOR, "%s: bad mode %d", fn, mode);
+  VODB_REQUIRE(nq == 0 || (out_scores != nullptr && out_idx != nullptr), "%s: output pointer is NULL", fn);
+  return VODB_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -521,14 +567,9 @@ int64_t vodb_store_bytes(const vodb_store* s) {
 
 int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device, int nq, int k, int mode,
                 float* out_scores, int64_t* out_idx, int out_on_device, void* stream) {
-  VODB_REQUIRE(s != nullptr, "vodb_search: store is NULL");
-  VODB_REQUIRE(queries != nullptr || nq == 0, "vodb_search: queries is NULL");
-  VODB_REQUIRE(nq >= 0, "vodb_search: nq=%d < 0", nq);
-  VODB_REQUIRE(k >= 1 && k <= VODB_MAX_K, "vodb_search: k=%d outside [1, %d]", k, VODB_MAX_K);
-  VODB_REQUIRE(q_dtype == VODB_F32 || q_dtype == VODB_BF16 || q_dtype == VODB_F16, "vodb_search: bad query dtype %d", q_dtype);
-  VODB_REQUIRE(mode == VODB_MODE_EXACT || mode == VODB_MODE_TENSOR, "vodb_search: bad mode %d", mode);
+  int rc = check_search_args(s, queries, q_dtype, nq, k, mode, out_scores, out_idx, "vodb_search");
+  if (rc != VODB_OK) return rc;
   if (nq == 0) return VODB_OK;
-  VODB_REQUIRE(out_scores != nullptr && out_idx != nullptr, "vodb_search: output pointer is NULL");
   if (s->n_added <= 0) {
     set_error("vodb_search: the store is empty (faiss health check: 'ERROR: Index is empty')");
     return VODB_ESTATE;
@@ -539,20 +580,10 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
   }
   DeviceGuard guard(s->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int rc = ensure_workspace(s, nq, k, dtype_size(q_dtype));
+  rc = ensure_workspace(s, nq, k, dtype_size(q_dtype));
   if (rc != VODB_OK) return rc;
   Workspace& w = s->ws;
-
-  // stage queries: host -> device copy if needed, then convert/pad to [nq_pad, pitch] of the scoring dtype
-  const void* q_dev = queries;
-  if (!q_on_device) {
-    VODB_CUDA_CHECK(cudaMemcpyAsync(w.q_in, queries, (size_t)nq * s->dim * dtype_size(q_dtype), cudaMemcpyHostToDevice, st));
-    q_dev = w.q_in;
-  }
-  const int stage_dtype = (mode == VODB_MODE_TENSOR) ? s->dtype : VODB_F32;
-  size_t rows_pad = ((size_t)nq + 255) / 256 * 256;
-  VODB_CUDA_CHECK(cudaMemsetAsync(w.q_stage, 0, rows_pad * s->pitch * dtype_size(stage_dtype), st));
-  rc = launch_convert_rows(q_dev, q_dtype, s->dim, w.q_stage, stage_dtype, s->pitch, nq, st);
+  rc = stage_queries(s, queries, q_dtype, q_on_device, nq, mode, st);
   if (rc != VODB_OK) return rc;
 
   float* o_s = out_on_device ? out_scores : w.out_s;
@@ -576,6 +607,131 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
     }
     safe = true;  // re-run with segments that cannot overflow
   }
+  if (!out_on_device) {
+    VODB_CUDA_CHECK(cudaMemcpyAsync(out_scores, w.out_s, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    VODB_CUDA_CHECK(cudaMemcpyAsync(out_idx, w.out_i, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VODB_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  return VODB_OK;
+}
+
+int vodb_xchg_create(vodb_xchg** out, int device, int rank, int world, int max_nq, int max_k,
+                     unsigned char* handle_out) {
+  VODB_REQUIRE(out != nullptr && handle_out != nullptr, "vodb_xchg_create: NULL argument");
+  *out = nullptr;
+  VODB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "vodb_xchg_create: bad rank %d / world %d (max %d)", rank, world, kMaxPeers);
+  VODB_REQUIRE(max_nq >= 1 && max_k >= 1 && max_k <= VODB_MAX_K, "vodb_xchg_create: bad max_nq / max_k");
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    set_error("cudaSetDevice(%d) failed", device);
+    return VODB_ECUDA;
+  }
+  vodb_xchg* x = new (std::nothrow) vodb_xchg();
+  if (!x) return VODB_ENOMEM;
+  x->device = device; x->rank = rank; x->world = world; x->max_nq = max_nq; x->max_k = max_k;
+  x->slot = (size_t)max_nq * max_k;
+  x->bytes = x->off_i() + (size_t)2 * world * x->slot * sizeof(int64_t);
+  cudaError_t e = cudaMalloc(&x->local, x->bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&x->done_counter, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(x->done_counter, 0, sizeof(int));
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, x->local);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("vodb_xchg_create: %s", cudaGetErrorString(e));
+    if (x->local) cudaFree(x->local);
+    if (x->done_counter) cudaFree(x->done_counter);
+    delete x;
+    cudaGetLastError();
+    return VODB_ECUDA;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == VODB_IPC_HANDLE_BYTES, "IPC handle size");
+  std::memcpy(handle_out, &h, VODB_IPC_HANDLE_BYTES);
+  x->peer[rank] = x->local;
+  *out = x;
+  return VODB_OK;
+}
+
+int vodb_xchg_connect(vodb_xchg* x, const unsigned char* all_handles) {
+  VODB_REQUIRE(x != nullptr && all_handles != nullptr, "vodb_xchg_connect: NULL argument");
+  DeviceGuard guard(x->device);
+  for (int r = 0; r < x->world; ++r) {
+    if (r == x->rank || x->peer[r]) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, all_handles + (size_t)r * VODB_IPC_HANDLE_BYTES, VODB_IPC_HANDLE_BYTES);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_error("vodb_xchg_connect: cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+      cudaGetLastError();
+      return VODB_ECUDA;
+    }
+    x->peer[r] = reinterpret_cast<char*>(ptr);
+  }
+  x->connected = true;
+  return VODB_OK;
+}
+
+void vodb_xchg_destroy(vodb_xchg* x) {
+  if (!x) return;
+  DeviceGuard guard(x->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < x->world; ++r)
+    if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
+  if (x->local) cudaFree(x->local);
+  if (x->done_counter) cudaFree(x->done_counter);
+  delete x;
+}
+
+int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_dtype, int q_on_device, int nq, int k,
+                        int mode, int safe, float* out_scores, int64_t* out_idx, int out_on_device, void* stream) {
+  int rc = check_search_args(s, queries, q_dtype, nq, k, mode, out_scores, out_idx, "vodb_search_sharded");
+  if (rc != VODB_OK) return rc;
+  VODB_REQUIRE(x != nullptr && x->connected, "vodb_search_sharded: exchange is NULL or not connected");
+  VODB_REQUIRE(x->device == s->device, "vodb_search_sharded: exchange and store live on different devices");
+  VODB_REQUIRE(nq >= 1 && (size_t)nq * k <= x->slot, "vodb_search_sharded: nq*k=%lld exceeds the exchange slot (%zu)", (long long)nq * k, x->slot);
+  if (mode == VODB_MODE_TENSOR && !tensor_path_supported(s)) {
+    set_error("vodb_search_sharded: VODB_MODE_TENSOR needs a bf16/f16 store");
+    return VODB_EUNSUPPORTED;
+  }
+  DeviceGuard guard(s->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  rc = ensure_workspace(s, nq, k, dtype_size(q_dtype));
+  if (rc != VODB_OK) return rc;
+  Workspace& w = s->ws;
+  rc = stage_queries(s, queries, q_dtype, q_on_device, nq, mode, st);
+  if (rc != VODB_OK) return rc;
+
+  // every rank calls this the same number of times: the epoch (and its parity = buffer half) stay in lockstep
+  x->epoch += 1;
+  const int parity = (int)(x->epoch & 1u);
+  ExchangeDst xd{};
+  xd.world = x->world;
+  xd.rank = x->rank;
+  xd.epoch = x->epoch;
+  xd.done_counter = x->done_counter;
+  for (int r = 0; r < x->world; ++r) {
+    char* base = x->peer[r];
+    xd.peer_s[r] = reinterpret_cast<float*>(base + x->off_s()) + ((size_t)parity * x->world + x->rank) * x->slot;
+    xd.peer_i[r] = reinterpret_cast<int64_t*>(base + x->off_i()) + ((size_t)parity * x->world + x->rank) * x->slot;
+    xd.peer_flag[r] = reinterpret_cast<uint32_t*>(base + x->off_flags()) + parity * kMaxPeers + x->rank;
+  }
+  if (s->n_added > 0) {
+    rc = run_scan(s, w.q_stage, nq, k, mode, safe != 0, nullptr, nullptr, st, &xd);
+  } else {
+    // an empty shard (more ranks than row blocks) contributes an all-padding list
+    VODB_CUDA_CHECK(cudaMemsetAsync(w.cnt, 0, (size_t)nq * sizeof(int), st));
+    rc = launch_select(w.cand_s, w.cand_i, w.cnt, w.tau, w.cap, nq, k, true, nullptr, nullptr, s->row_offset, st, &xd);
+  }
+  if (rc != VODB_OK) return rc;
+  float* o_s = out_on_device ? out_scores : w.out_s;
+  int64_t* o_i = out_on_device ? out_idx : w.out_i;
+  const float* gs = reinterpret_cast<const float*>(x->local + x->off_s()) + (size_t)parity * x->world * x->slot;
+  const int64_t* gi = reinterpret_cast<const int64_t*>(x->local + x->off_i()) + (size_t)parity * x->world * x->slot;
+  const uint32_t* flags = reinterpret_cast<const uint32_t*>(x->local + x->off_flags()) + parity * kMaxPeers;
+  rc = launch_merge_exchange(gs, gi, flags, x->epoch, x->world, x->slot, nq, k, o_s, o_i, st);
+  if (rc != VODB_OK) return rc;
   if (!out_on_device) {
     VODB_CUDA_CHECK(cudaMemcpyAsync(out_scores, w.out_s, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
     VODB_CUDA_CHECK(cudaMemcpyAsync(out_idx, w.out_i, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));

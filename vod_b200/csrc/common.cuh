@@ -137,13 +137,32 @@ struct SegmentArgs {
   bool dump;            // first segment of a scan: lists are empty, every score is stored at slot row-row_begin
 };
 
+// Cross-shard exchange fused into the final select (select.cu): every rank's final select kernel stores its [nq,k]
+// result straight into slot `rank` of every peer's gather buffer (peer-mapped memory, NVLink stores), the last CTA
+// publishes an epoch flag on every peer, and the merge kernel spins on its own flags before reducing world*k -> k.
+constexpr int kMaxPeers = 16;
+struct ExchangeDst {
+  int world;
+  int rank;
+  uint32_t epoch;
+  int* done_counter;                 // local: CTAs of the final select that have finished their stores
+  float* peer_s[kMaxPeers];          // peer r's gather scores, slot `rank`, current parity
+  int64_t* peer_i[kMaxPeers];
+  uint32_t* peer_flag[kMaxPeers];    // peer r's flags[parity][rank]
+};
+
 int launch_score_exact(const SegmentArgs& a, int sm_count, cudaStream_t stream);
 int launch_score_tensor(vodb_store* s, const SegmentArgs& a, cudaStream_t stream);
 bool tensor_path_supported(const vodb_store* s);
 
 // select the k best candidates of every query list; if `final`, sort and write outputs
 int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap, int nq, int k, bool final,
-                  float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream);
+                  float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream,
+                  const ExchangeDst* xd = nullptr);
+// merge of the gathered per-rank lists after waiting for every peer's epoch flag (see ExchangeDst)
+int launch_merge_exchange(const float* gather_s, const int64_t* gather_i, const uint32_t* flags, uint32_t epoch,
+                          int world, size_t slot_elems, int nq, int k, float* out_s, int64_t* out_i,
+                          cudaStream_t stream);
 int launch_merge(const float* scores, const int64_t* idx, int n_lists, int nq, int k_in, int k_out, float* out_s,
                  int64_t* out_i, cudaStream_t stream);
 int launch_init_lists(int* cnt, float* tau, int first_rows, int nq, cudaStream_t stream);

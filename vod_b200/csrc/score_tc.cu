@@ -378,24 +378,34 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
                  (__uint_as_float(v[j4 * 4 + 2]) >= t.z) | (__uint_as_float(v[j4 * 4 + 3]) >= t.w);
         }
         any = any && valid;
-        {
-          if (any) {
-            // rare: push survivors into the CTA's shared staging buffer (shared-memory atomics only); the global
-            // list append (one L2 atomic round trip per entry) is done in bulk by flush_staged, 128 threads wide
+        if (any) {
+          // rare, divergent: this lane (= corpus row) has survivors among the 32 query columns. Build the column
+          // bitmask from registers (thresholds re-read as 8 x LDS.128, before any store), reserve the staging slots
+          // with ONE shared-memory atomic, then write the entries. The global list append (one L2 atomic round trip
+          // per entry) is done in bulk by flush_issue / flush_complete, 128 threads wide.
+          uint32_t m = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float s = __uint_as_float(v[j]);
-              if (s >= tau_cur[c0 + j]) {
-                const int q = q0 + c0 + j;
-                const int idx = atomicAdd(&stg.count[sb], 1);
-                if (idx < kStageCap) {
-                  stg.s[sb][idx] = s;
-                  stg.row[sb][idx] = (int32_t)row;
-                  stg.q[sb][idx] = q;
-                } else {
-                  append_global(p, q, s, (int32_t)row);  // staging full: slow but correct
-                }
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 t = *reinterpret_cast<const float4*>(tau_cur + c0 + j4 * 4);
+            m |= (__uint_as_float(v[j4 * 4 + 0]) >= t.x ? 1u : 0u) << (j4 * 4 + 0);
+            m |= (__uint_as_float(v[j4 * 4 + 1]) >= t.y ? 1u : 0u) << (j4 * 4 + 1);
+            m |= (__uint_as_float(v[j4 * 4 + 2]) >= t.z ? 1u : 0u) << (j4 * 4 + 2);
+            m |= (__uint_as_float(v[j4 * 4 + 3]) >= t.w ? 1u : 0u) << (j4 * 4 + 3);
+          }
+          int idx = atomicAdd(&stg.count[sb], __popc(m));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (m & (1u << j)) {
+              const float sc = __uint_as_float(v[j]);
+              const int q = q0 + c0 + j;
+              if (idx < kStageCap) {
+                stg.s[sb][idx] = sc;
+                stg.row[sb][idx] = (int32_t)row;
+                stg.q[sb][idx] = q;
+              } else {
+                append_global(p, q, sc, (int32_t)row);  // staging full: slow but correct
               }
+              ++idx;
             }
           }
         }

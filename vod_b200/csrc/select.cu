@@ -225,7 +225,7 @@ template <typename IdxT>
 __global__ void __launch_bounds__(kSelThreads)
 select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __restrict__ cnt, float* __restrict__ tau,
               int cap, int k, int P, int final_pass, float* __restrict__ out_s, int64_t* __restrict__ out_i,
-              int64_t row_offset) {
+              int64_t row_offset, const ExchangeDst xd, int use_xd) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ SelectSmem<int32_t> sm;
   int32_t* sel_i = reinterpret_cast<int32_t*>(dyn);
@@ -241,7 +241,28 @@ select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __r
   uint32_t vstar;
   int n_sel = block_select<int32_t>(load, n, k, final_pass != 0, sm, sel_o, sel_i, P, &vstar);
   __syncthreads();
-  if (final_pass) {
+  if (final_pass && use_xd) {
+    // fused exchange: store this shard's result into every rank's gather buffer (own rank included)
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      const float sv = (j < n_sel) ? ord_to_float(sel_o[j]) : VODB_NEG_FLT_MAX;
+      const int64_t iv = (j < n_sel) ? (int64_t)sel_i[j] + row_offset : (int64_t)-1;
+      for (int r = 0; r < xd.world; ++r) {
+        xd.peer_s[r][(size_t)q * k + j] = sv;
+        xd.peer_i[r][(size_t)q * k + j] = iv;
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int done = atomicAdd(xd.done_counter, 1);
+      if (done == (int)gridDim.x - 1) {  // last CTA: every CTA's stores are fenced; publish the epoch on every peer
+        *xd.done_counter = 0;
+        __threadfence_system();
+        for (int r = 0; r < xd.world; ++r)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xd.peer_flag[r]), "r"(xd.epoch) : "memory");
+      }
+    }
+  } else if (final_pass) {
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
       if (j < n_sel) {
         out_s[(size_t)q * k + j] = ord_to_float(sel_o[j]);
@@ -288,6 +309,46 @@ merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, 
   }
 }
 
+// Merge after the fused exchange: wait until every source rank has published `epoch`, then reduce world*k -> k.
+__global__ void __launch_bounds__(kSelThreads)
+merge_exchange_kernel(const float* __restrict__ gather_s, const int64_t* __restrict__ gather_i,
+                      const uint32_t* __restrict__ flags, uint32_t epoch, int world, size_t slot_elems, int nq, int k,
+                      int P, float* __restrict__ out_s, int64_t* __restrict__ out_i) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ SelectSmem<int64_t> sm;
+  int64_t* sel_i = reinterpret_cast<int64_t*>(dyn);
+  uint32_t* sel_o = reinterpret_cast<uint32_t*>(dyn + (size_t)P * sizeof(int64_t));
+  if ((int)threadIdx.x < world) {
+    uint32_t v;
+    unsigned long long spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+      if ((int32_t)(v - epoch) >= 0) break;
+      if (++spins > (1ull << 31)) {  // a peer never arrived: fail loudly instead of hanging the GPU
+        printf("vodb: exchange timeout waiting for rank %d (epoch %u, flag %u)\n", (int)threadIdx.x, epoch, v);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  const int q = blockIdx.x;
+  const int n = world * k;
+  auto load = [&](int i, float& s, int64_t& id) {
+    int l = i / k, j = i - l * k;
+    size_t off = (size_t)l * slot_elems + (size_t)q * k + j;
+    s = gather_s[off];
+    id = gather_i[off];
+  };
+  uint32_t vstar;
+  int n_sel = block_select<int64_t>(load, n, k, true, sm, sel_o, sel_i, P, &vstar);
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    bool ok = j < n_sel && sel_i[j] >= 0;
+    out_s[(size_t)q * k + j] = ok ? ord_to_float(sel_o[j]) : VODB_NEG_FLT_MAX;
+    out_i[(size_t)q * k + j] = ok ? sel_i[j] : -1;
+  }
+}
+
 // cnt starts at the row count of the first scan segment: that segment stores every score at slot row-row_begin
 // ("dump" mode of the scoring kernels), so the lists are pre-sized instead of grown with atomics.
 // The overflow flag is sticky: cleared by the host after it has been read (vodb_search / vodb_search_check).
@@ -308,11 +369,24 @@ int launch_init_lists(int* cnt, float* tau, int first_rows, int nq, cudaStream_t
 }
 
 int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap, int nq, int k, bool final_pass,
-                  float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream) {
+                  float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream, const ExchangeDst* xd) {
   int P = pow2ceil(k);
   size_t smem = (size_t)P * (sizeof(int32_t) + sizeof(uint32_t));
+  ExchangeDst none{};
   select_kernel<int32_t><<<nq, kSelThreads, smem, stream>>>(cand_s, cand_i, cnt, tau, cap, k, P, final_pass ? 1 : 0,
-                                                            out_s, out_i, row_offset);
+                                                            out_s, out_i, row_offset, xd ? *xd : none,
+                                                            (xd && final_pass) ? 1 : 0);
+  VODB_CUDA_CHECK(cudaGetLastError());
+  return VODB_OK;
+}
+
+int launch_merge_exchange(const float* gather_s, const int64_t* gather_i, const uint32_t* flags, uint32_t epoch,
+                          int world, size_t slot_elems, int nq, int k, float* out_s, int64_t* out_i,
+                          cudaStream_t stream) {
+  int P = pow2ceil(k);
+  size_t smem = (size_t)P * (sizeof(int64_t) + sizeof(uint32_t));
+  merge_exchange_kernel<<<nq, kSelThreads, smem, stream>>>(gather_s, gather_i, flags, epoch, world, slot_elems, nq, k, P,
+                                                           out_s, out_i);
   VODB_CUDA_CHECK(cudaGetLastError());
   return VODB_OK;
 }

@@ -6,10 +6,16 @@ scans its own rows, per-GPU top-k lists are merged on the host. Here every rank 
 the contiguous row block `shard_bounds(n_total, world, rank)`; a search is
 
     local top-k on every rank (global ids = row_offset + local row, cf. sharded_search.py:103 `indices += offset`)
-    -> one all-gather of the [B,k] scores and ids over NCCL/NVLink
-    -> `vodb_merge_topk` (radix select + bitonic sort on the GPU) on every rank.
+    -> exchange of the [B,k] scores and ids between the ranks
+    -> merge (radix select + bitonic sort on the GPU) on every rank.
 
-The only data-path collective is that all-gather: B*k*12 bytes per rank (77 KB at B=64, k=100).
+Two exchange implementations, same results:
+  * exchange="p2p" (default on GPUs): fused into the kernels. The final select kernel of every rank stores its list
+    straight into every peer's gather buffer (CUDA-IPC peer-mapped memory, NVLink stores) and publishes an epoch
+    flag; the merge kernel spins on its own flags. No collective library call, no extra launch
+    (`vodb_search_sharded`, include/vodb.h).
+  * exchange="nccl": one `all_gather_into_tensor` per array over NCCL, then `vodb_merge_topk`.
+The exchanged payload is B*k*12 bytes per rank (77 KB at B=64, k=100).
 """
 from __future__ import annotations
 
@@ -71,7 +77,8 @@ class ShardedCorpus:
     """This rank's shard of an `n_total x dim` corpus plus the cross-shard search."""
 
     def __init__(self, n_total: int, dim: int, dtype: str = "bfloat16", device: int = 0, group: typ.Any = None,
-                 rank: int | None = None, world_size: int | None = None):
+                 rank: int | None = None, world_size: int | None = None, exchange: str = "p2p",
+                 max_queries: int = 8192, max_k: int = 1000):
         import torch.distributed as dist
 
         from .search import CorpusStore, merge_topk_device
@@ -88,6 +95,35 @@ class ShardedCorpus:
         self.mode: str | None = None
         self._searcher = ShardedSearcher(lambda q, k: self.store.search_device(q, k, mode=self.mode),
                                          merge_topk_device, group)
+        self.group = group
+        self.exchange = exchange if world_size > 1 else "none"
+        self._xchg = None
+        self._xchg_limits = (max_queries, max_k)
+        if self.exchange == "p2p":
+            self._setup_p2p(device, max_queries, max_k)
+
+    def _setup_p2p(self, device: int, max_queries: int, max_k: int) -> None:
+        """Create this rank's peer-mapped exchange buffer and connect to the peers' (CUDA IPC handles are
+        all-gathered with torch.distributed)."""
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        lib = _lib.load()
+        handle = (ctypes.c_ubyte * 64)()
+        x = ctypes.c_void_p()
+        _lib.check(lib.vodb_xchg_create(ctypes.byref(x), device, self.rank, self.world, max_queries, max_k, handle),
+                   "vodb_xchg_create")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=f"cuda:{device}")
+        everyone = torch.empty(self.world * 64, dtype=torch.uint8, device=f"cuda:{device}")
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        blob = bytes(everyone.cpu().tolist())
+        _lib.check(lib.vodb_xchg_connect(x, blob), "vodb_xchg_connect")
+        dist.barrier(group=self.group)
+        self._xchg = x
 
     def fill_synthetic(self, seed: int, unit_norm: bool = False) -> None:
         """Every rank generates its own rows of the same global synthetic corpus (ids are global)."""
@@ -99,9 +135,51 @@ class ShardedCorpus:
         if a < b:
             self.store.add(rows[a - row0:b - row0], row0=a - self.lo)
 
-    def search_device(self, queries: typ.Any, top_k: int, mode: str | None = None):
+    def search_device(self, queries: typ.Any, top_k: int, mode: str | None = None, safe: bool = False, out=None):
+        """Merged top-k over all shards for CUDA queries; returns (scores [B,k] f32, ids [B,k] i64) CUDA tensors,
+        identical on every rank. Only enqueues work on torch's current stream."""
         self.mode = mode
-        return self._searcher.search(queries, top_k)
+        if self.exchange != "p2p":
+            return self._searcher.search(queries, top_k)
+        import torch
+
+        from . import _lib
+        from .search import _current_stream_ptr, _torch_info
+
+        ptr, code, is_cuda, dev = _torch_info(queries)
+        if not is_cuda or dev != self.store.device:
+            raise ValueError(f"search_device needs a tensor on cuda:{self.store.device}")
+        B = int(queries.shape[0])
+        if B * top_k > self._xchg_limits[0] * self._xchg_limits[1]:
+            raise ValueError("batch x top_k exceeds the exchange buffer (raise max_queries / max_k)")
+        if out is None:
+            scores = torch.empty((B, top_k), dtype=torch.float32, device=queries.device)
+            ids = torch.empty((B, top_k), dtype=torch.int64, device=queries.device)
+        else:
+            scores, ids = out
+        lib = _lib.load()
+        _lib.check(lib.vodb_search_sharded(self.store.handle, self._xchg, ptr, code, 1, B, int(top_k),
+                                           self.store._mode(mode), int(safe), scores.data_ptr(), ids.data_ptr(), 1,
+                                           _current_stream_ptr(self.store.device)), "vodb_search_sharded")
+        return scores, ids
+
+    def any_overflow(self) -> bool:
+        """True if a candidate list overflowed on ANY rank since the last check (then re-run with safe=True)."""
+        import torch
+        import torch.distributed as dist
+
+        flag = torch.tensor([1 if self.store.check_async() else 0], dtype=torch.int32, device=f"cuda:{self.store.device}")
+        if self.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        return bool(flag.item())
 
     def close(self) -> None:
+        if self._xchg is not None:
+            import torch.distributed as dist
+
+            from . import _lib
+
+            dist.barrier(group=self.group)  # nobody may still be storing into this rank's buffer
+            _lib.load().vodb_xchg_destroy(self._xchg)
+            self._xchg = None
         self.store.close()
