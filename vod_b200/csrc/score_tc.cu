@@ -144,50 +144,51 @@ struct TcParams {
   int dump;  // first segment: store every score at slot (row - row_begin) instead of filtering
 };
 
-// CTA-level staging of filter survivors (shared memory): pushed with shared-memory atomics by the epilogue
-// threads, appended to the global per-query lists in bulk so that the L2 atomic latency (~0.7 us) is paid once
-// per batch of entries instead of once per surviving score.
-constexpr int kStageCap = 512;
-struct StageBuf {
+// Per-warp staging of filter survivors (shared memory). Each epilogue warp owns two small buffers: survivors of
+// item i are pushed with shared-memory atomics into buffer i&1 and appended to the global per-query lists at the
+// start of item i+1 by the same warp, 32 lanes wide, so the L2 atomic round trip (microseconds when the L2 is
+// saturated by the operand stream) is paid once per batch of entries and overlaps the next item's work. Nothing is
+// shared between the four epilogue warps: they never synchronise with each other.
+constexpr int kWarpStageCap = 128;
+struct WarpStage {
   int count[2];
   int pad[2];
-  float s[2][kStageCap];
-  int32_t row[2][kStageCap];
-  int32_t q[2][kStageCap];
+  float s[2][kWarpStageCap];
+  int32_t row[2][kWarpStageCap];
+  int32_t q[2][kWarpStageCap];
 };
 
-__device__ __forceinline__ void append_global(const TcParams& p, int q, float s, int32_t row) {
-  const int pos = atomicAdd(&p.cnt[q], 1);
-  if (pos < p.cap) {
-    p.cand_s[(size_t)q * p.cap + pos] = s;
-    p.cand_i[(size_t)q * p.cap + pos] = row;
+__device__ __noinline__ void append_global(int* cnt, float* cand_s, int32_t* cand_i, int* overflow, int cap, int q,
+                                           float s, int32_t row) {
+  const int pos = atomicAdd(&cnt[q], 1);
+  if (pos < cap) {
+    cand_s[(size_t)q * cap + pos] = s;
+    cand_i[(size_t)q * cap + pos] = row;
   } else {
-    *p.overflow = 1;
+    *overflow = 1;
   }
 }
 
-// Bulk append of the staged entries of buffer `b` to the global lists by the 128 epilogue threads, split in two
-// halves so that the L2 atomic round trip (several microseconds when the L2 is saturated by the operand stream)
-// overlaps the next item's epilogue work: `issue` copies the entries to registers and fires the slot-reserving
-// atomics, `complete` (called after the item's score columns have been processed) consumes the slots.
-constexpr int kFlushPerThread = kStageCap / 128;
+// `issue` copies the staged entries of buffer `b` to registers and fires the slot-reserving atomics; `complete`
+// (called after the item's score columns have been processed) consumes the slots.
+constexpr int kFlushPerLane = kWarpStageCap / 32;
 struct PendingFlush {
-  float s[kFlushPerThread];
-  int32_t row[kFlushPerThread];
-  int32_t q[kFlushPerThread];
-  int pos[kFlushPerThread];
+  float s[kFlushPerLane];
+  int32_t row[kFlushPerLane];
+  int32_t q[kFlushPerLane];
+  int pos[kFlushPerLane];
 };
 
-__device__ __forceinline__ void flush_issue(const TcParams& p, const StageBuf& stg, int b, int et, PendingFlush& f) {
-  const int n = min(stg.count[b], kStageCap);
+__device__ __forceinline__ void flush_issue(const TcParams& p, const WarpStage& ws, int b, int lane, PendingFlush& f) {
+  const int n = min(ws.count[b], kWarpStageCap);
 #pragma unroll
-  for (int u = 0; u < kFlushPerThread; ++u) {
-    const int e = et + u * 128;
+  for (int u = 0; u < kFlushPerLane; ++u) {
+    const int e = lane + u * 32;
     f.pos[u] = -1;
     if (e < n) {
-      f.s[u] = stg.s[b][e];
-      f.row[u] = stg.row[b][e];
-      f.q[u] = stg.q[b][e];
+      f.s[u] = ws.s[b][e];
+      f.row[u] = ws.row[b][e];
+      f.q[u] = ws.q[b][e];
       f.pos[u] = atomicAdd(&p.cnt[f.q[u]], 1);
     }
   }
@@ -195,7 +196,7 @@ __device__ __forceinline__ void flush_issue(const TcParams& p, const StageBuf& s
 
 __device__ __forceinline__ void flush_complete(const TcParams& p, PendingFlush& f) {
 #pragma unroll
-  for (int u = 0; u < kFlushPerThread; ++u) {
+  for (int u = 0; u < kFlushPerLane; ++u) {
     if (f.pos[u] >= 0) {
       if (f.pos[u] < p.cap) {
         p.cand_s[(size_t)f.q[u] * p.cap + f.pos[u]] = f.s[u];
@@ -208,6 +209,20 @@ __device__ __forceinline__ void flush_complete(const TcParams& p, PendingFlush& 
   }
 }
 
+// v[j] for a run-time j (registers cannot be indexed dynamically): 5-level select tree, 31 SEL, no branches
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+  return (j & 16) ? d[1] : d[0];
+}
+
 template <int BN>
 struct TcConfig {
   static constexpr uint32_t kABytes = BM * KC * 2;
@@ -217,7 +232,7 @@ struct TcConfig {
   static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                         : (2 * BN <= 256) ? 256 : 512;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                         2 * BN * sizeof(float) /*tau*/ + sizeof(StageBuf);
+                                         4 * BN * sizeof(float) /*tau, one copy per epilogue warp*/ + 4 * sizeof(WarpStage);
 };
 
 template <int BN>
@@ -237,8 +252,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* tau_s = reinterpret_cast<float*>(bars + 2 * STAGES + 6);  // [2][BN]
-  StageBuf& stg = *reinterpret_cast<StageBuf*>(tau_s + 2 * BN);
+  float* tau_s = reinterpret_cast<float*>(bars + 2 * STAGES + 6);  // [4 epilogue warps][BN]
+  WarpStage* wst = reinterpret_cast<WarpStage*>(tau_s + 4 * BN);   // [4 epilogue warps]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -252,8 +267,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 4);
     }
-    stg.count[0] = 0;
-    stg.count[1] = 0;
+    for (int w = 0; w < 4; ++w) wst[w].count[0] = wst[w].count[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -319,30 +333,34 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       }
     }
   } else {
-    // ---------------- epilogue warps (2..5) ----------------
+    // ---------------- epilogue warps (2..5): independent of each other ----------------
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64;  // 0..127
+    const int ew = warp - 2;
+    WarpStage& ws = wst[ew];
+    float* tau_cur = tau_s + ew * BN;
     int local = 0;
     PendingFlush pend;
 #pragma unroll
-    for (int u = 0; u < kFlushPerThread; ++u) pend.pos[u] = -1;
+    for (int u = 0; u < kFlushPerLane; ++u) pend.pos[u] = -1;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
       const int ct = item / p.n_qtiles, qt = item - ct * p.n_qtiles;
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int q0 = qt * BN;
       const int sb = local & 1;  // staging buffer that receives this item's survivors
-      float* tau_cur = tau_s + acc * BN;
-      // (A) every epilogue thread has finished pushing the previous item's survivors
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       if (!p.dump) {
-        if (local > 0) flush_issue(p, stg, sb ^ 1, et, pend);
-        // stage this query tile's thresholds (queries past nq never pass)
-        for (int c = et; c < BN; c += 128) tau_cur[c] = (q0 + c < p.nq) ? p.tau[q0 + c] : INFINITY;
+        // append the previous item's survivors (atomics fired now, slots consumed after this item's columns)
+        if (local > 0) flush_issue(p, ws, sb ^ 1, lane, pend);
+        // this query tile's thresholds (queries past nq never pass)
+        if (q0 + BN <= p.nq) {
+          for (int c = lane * 4; c < BN; c += 128)
+            *reinterpret_cast<float4*>(tau_cur + c) = *reinterpret_cast<const float4*>(p.tau + q0 + c);
+        } else {
+          for (int c = lane; c < BN; c += 32) tau_cur[c] = (q0 + c < p.nq) ? p.tau[q0 + c] : INFINITY;
+        }
       }
-      // (B) everybody has read the flushed buffer's count; its counter may be reset (next pushed to after the next (A))
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et == 0) stg.count[sb ^ 1] = 0;
+      __syncwarp();
+      if (lane == 0) ws.count[sb ^ 1] = 0;  // every lane has read it; next pushed to two items from now
 
       const int64_t row = p.row_begin + (int64_t)ct * BM + quarter * 32 + lane;
       const bool valid = row < p.row_end;
@@ -377,12 +395,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
           any |= (__uint_as_float(v[j4 * 4 + 0]) >= t.x) | (__uint_as_float(v[j4 * 4 + 1]) >= t.y) |
                  (__uint_as_float(v[j4 * 4 + 2]) >= t.z) | (__uint_as_float(v[j4 * 4 + 3]) >= t.w);
         }
-        any = any && valid;
-        if (any) {
+        if (any && valid) {
           // rare, divergent: this lane (= corpus row) has survivors among the 32 query columns. Build the column
-          // bitmask from registers (thresholds re-read as 8 x LDS.128, before any store), reserve the staging slots
-          // with ONE shared-memory atomic, then write the entries. The global list append (one L2 atomic round trip
-          // per entry) is done in bulk by flush_issue / flush_complete, 128 threads wide.
+          // bitmask from registers, reserve staging slots with ONE shared-memory atomic, then push each set bit.
           uint32_t m = 0;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
@@ -392,21 +407,21 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
             m |= (__uint_as_float(v[j4 * 4 + 2]) >= t.z ? 1u : 0u) << (j4 * 4 + 2);
             m |= (__uint_as_float(v[j4 * 4 + 3]) >= t.w ? 1u : 0u) << (j4 * 4 + 3);
           }
-          int idx = atomicAdd(&stg.count[sb], __popc(m));
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (m & (1u << j)) {
-              const float sc = __uint_as_float(v[j]);
-              const int q = q0 + c0 + j;
-              if (idx < kStageCap) {
-                stg.s[sb][idx] = sc;
-                stg.row[sb][idx] = (int32_t)row;
-                stg.q[sb][idx] = q;
-              } else {
-                append_global(p, q, sc, (int32_t)row);  // staging full: slow but correct
-              }
-              ++idx;
+          int idx = atomicAdd(&ws.count[sb], __popc(m));
+#pragma unroll 1
+          while (m != 0u) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1u;
+            const float sc = __uint_as_float(pick32(v, j));
+            const int q = q0 + c0 + j;
+            if (idx < kWarpStageCap) {
+              ws.s[sb][idx] = sc;
+              ws.row[sb][idx] = (int32_t)row;
+              ws.q[sb][idx] = q;
+            } else {
+              append_global(p.cnt, p.cand_s, p.cand_i, p.overflow, p.cap, q, sc, (int32_t)row);  // staging full: slow, correct
             }
+            ++idx;
           }
         }
       }
@@ -416,9 +431,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       flush_complete(p, pend);  // slots reserved at the top of this item have arrived by now
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    __syncwarp();
     if (!p.dump && local > 0) {
-      flush_issue(p, stg, (local - 1) & 1, et, pend);
+      flush_issue(p, ws, (local - 1) & 1, lane, pend);
       flush_complete(p, pend);
     }
   }
