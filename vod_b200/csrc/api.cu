@@ -283,7 +283,7 @@ void free_workspace(Workspace& w) {
 }
 
 // row segments [b_i, b_{i+1}) of the scan; boundaries are multiples of 128 (except the end)
-std::vector<int64_t> plan_segments(int64_t n, int cap, int k, bool safe) {
+std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe) {
   std::vector<int64_t> b;
   b.push_back(0);
   auto round128 = [](int64_t x) { return std::max<int64_t>(128, x / 128 * 128); };
@@ -293,14 +293,18 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, bool safe) {
     b.push_back(n);
     return b;
   }
-  int64_t first = round128(cap / 2);
+  // Large batches refresh the thresholds more often (smaller first segment, growth 3 instead of up to 32): the
+  // number of survivors per query over the whole scan is ~ k*g*log_{1+g}(n/first), every survivor costs epilogue
+  // time, and with thousands of queries that outweighs the fixed cost of a few more (select + launch) pairs.
+  const bool large_batch = nq > 256;
+  int64_t first = round128(large_batch ? std::min(cap / 2, 4096) : cap / 2);
   if (first >= n) {
     b.push_back(n);
     return b;
   }
   b.push_back(first);
   // growth: expected survivors of a segment = k * seg/before; keep that below cap/8
-  double g = std::max(1.0, (double)cap / (8.0 * k));
+  double g = std::max(1.0, std::min((double)cap / (8.0 * k), large_batch ? 3.0 : 32.0));
   int64_t cur = first;
   while (cur < n) {
     int64_t seg = round128((int64_t)(g * (double)cur));
@@ -315,7 +319,7 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, bool safe) {
 int run_scan(vodb_store* s, const void* q_stage, int nq, int k, int mode, bool safe, float* out_s, int64_t* out_i,
              cudaStream_t st, const ExchangeDst* xd = nullptr) {
   Workspace& w = s->ws;
-  std::vector<int64_t> b = plan_segments(s->n_added, w.cap, k, safe);
+  std::vector<int64_t> b = plan_segments(s->n_added, w.cap, k, nq, safe);
   // the first segment (<= cap/2 rows, or <= cap-k in safe mode) stores every score: lists start pre-sized
   int rc = launch_init_lists(w.cnt, w.tau, (int)(b[1] - b[0]), nq, st);
   if (rc != VODB_OK) return rc;
