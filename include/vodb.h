@@ -50,6 +50,8 @@ extern "C" {
 /* scoring modes of vodb_search */
 #define VODB_MODE_EXACT 0  /* fp32 FMA on CUDA cores over the stored values: IndexFlatIP parity mode */
 #define VODB_MODE_TENSOR 1 /* tcgen05 tensor cores (bf16/fp16 store; queries rounded to the store dtype) */
+#define VODB_MODE_TENSOR_X2 2 /* same, float32 queries split into 2 store-dtype terms (~16 mantissa bits kept) */
+#define VODB_MODE_TENSOR_X3 3 /* same, 3 terms: the full float32 query mantissa; products are exact in fp32 */
 
 /* error codes */
 #define VODB_OK 0

@@ -246,3 +246,47 @@ def test_error_paths():
     st.close()
     with pytest.raises(vod_b200.VodbError):
         st.search(np.zeros((1, 8), np.float32), 3)
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+def test_tensor_multi_term_queries_keep_fp32_query_precision(dtype):
+    """float32 (unrounded) queries against a 16-bit store. One term rounds the query to the store dtype; two / three
+    terms split it into hi + lo (+ lo2) parts accumulated in the same TMEM accumulator. Three bf16 terms carry the
+    full 24-bit mantissa: every product is exact in fp32, only the accumulation order differs from the oracle, so
+    the fp32-exact tolerance (1e-5 relative, near-tie swaps only) applies — IndexFlatIP parity on tensor cores."""
+    rng = np.random.default_rng(17)
+    xb = round_to(rng.standard_normal((300_000, 768), dtype=np.float32), dtype)
+    xq = rng.standard_normal((64, 768), dtype=np.float32)          # NOT representable in 16 bits
+    st = _store(xb, dtype)
+    rs, ri = flat_ip.search(xb, xq, 100)
+    recalls = {}
+    for mode in ("tensor", "tensor2", "tensor3"):
+        s, i = st.search(xq, 100, mode=mode)
+        recalls[mode] = flat_ip.recall_at_k(i, ri)
+        if mode == "tensor3":
+            rep = flat_ip.compare_topk(xb, xq, s, i, rs, ri, rtol=RTOL)
+            assert rep["ok"], rep
+    assert recalls["tensor2"] >= 0.999, recalls
+    assert recalls["tensor3"] >= 0.9995, recalls
+    assert recalls["tensor"] >= 0.95, recalls      # documented: rounding the query costs recall on near-ties
+    # larger batches use the 128-query tile variants
+    xq2 = rng.standard_normal((200, 768), dtype=np.float32)
+    rs2, ri2 = flat_ip.search(xb, xq2, 100)
+    for mode in ("tensor2", "tensor3"):
+        s, i = st.search(xq2, 100, mode=mode)
+        assert flat_ip.recall_at_k(i, ri2) >= 0.999
+    s, i = st.search(xq2, 100, mode="tensor3")
+    rep = flat_ip.compare_topk(xb, xq2, s, i, rs2, ri2, rtol=RTOL)
+    assert rep["ok"], rep
+    st.close()
+
+
+@pytest.mark.parametrize("mode", ["tensor2", "tensor3"])
+def test_multi_term_modes_bit_exact_on_integer_data(mode):
+    rng = np.random.default_rng(23)
+    xb, xq = int_valued(rng, (50_000, 200)), int_valued(rng, (130, 200))
+    st = _store(xb, "bfloat16")
+    s, i = st.search(xq, 64, mode=mode)
+    rs, ri = flat_ip.search(xb, xq, 64)
+    assert np.array_equal(i, ri) and np.array_equal(s, rs)
+    st.close()

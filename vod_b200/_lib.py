@@ -12,7 +12,7 @@ _PKG = pathlib.Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libvodb.so"
 
 F32, BF16, F16 = 0, 1, 2
-MODE_EXACT, MODE_TENSOR = 0, 1
+MODE_EXACT, MODE_TENSOR, MODE_TENSOR_X2, MODE_TENSOR_X3 = 0, 1, 2, 3
 QUIRK_INVERTED_SUPPORT = 1
 MAX_K = 2048
 DTYPE_NAMES = {"float32": F32, "f32": F32, "fp32": F32, "bfloat16": BF16, "bf16": BF16, "float16": F16, "f16": F16,

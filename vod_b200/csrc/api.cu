@@ -80,6 +80,25 @@ __global__ void convert_rows_kernel(const S* __restrict__ src, int src_dim, D* _
   }
 }
 
+// float32 query -> `terms` 16-bit planes: plane t = round(q - plane_0 - ... - plane_{t-1}). The partial sums are
+// exact in float32 (each remainder is a float32 with fewer significant bits), so 3 bf16 / 2-3 fp16 terms
+// reproduce the float32 value exactly (barring fp16 range limits).
+template <typename S, typename D>
+__global__ void split_rows_kernel(const S* __restrict__ src, int src_dim, D* __restrict__ dst, int dst_pitch, int64_t n,
+                                  int64_t plane_rows, int terms) {
+  int64_t total = n * dst_pitch;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = e / dst_pitch;
+    int c = (int)(e - r * dst_pitch);
+    float v = (c < src_dim) ? to_f32<S>(src[r * src_dim + c]) : 0.0f;
+    for (int t = 0; t < terms; ++t) {
+      D d = from_f32<D>(v);
+      dst[(size_t)t * plane_rows * dst_pitch + e] = d;
+      v = __fsub_rn(v, to_f32<D>(d));
+    }
+  }
+}
+
 template <typename D>
 __device__ __forceinline__ D round_store(float v);
 template <>
@@ -173,6 +192,35 @@ int launch_convert_rows(const void* src, int src_dtype, int src_dim, void* dst, 
   return VODB_EINVAL;
 }
 
+namespace {
+template <typename S>
+int split_dispatch_dst(const void* src, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
+                       int64_t plane_rows, int terms, cudaStream_t st) {
+  int64_t total = n * dst_pitch;
+  if (total == 0) return VODB_OK;
+  int g = grid_for(total);
+  const S* s = reinterpret_cast<const S*>(src);
+  switch (dst_dtype) {
+    case VODB_BF16: split_rows_kernel<S, __nv_bfloat16><<<g, 256, 0, st>>>(s, src_dim, (__nv_bfloat16*)dst, dst_pitch, n, plane_rows, terms); break;
+    case VODB_F16: split_rows_kernel<S, __half><<<g, 256, 0, st>>>(s, src_dim, (__half*)dst, dst_pitch, n, plane_rows, terms); break;
+    default: set_error("launch_split_rows: destination must be a 16-bit dtype, got %d", dst_dtype); return VODB_EINVAL;
+  }
+  VODB_CUDA_CHECK(cudaGetLastError());
+  return VODB_OK;
+}
+}  // namespace
+
+int launch_split_rows(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
+                      int64_t plane_rows, int terms, cudaStream_t st) {
+  switch (src_dtype) {
+    case VODB_F32: return split_dispatch_dst<float>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, st);
+    case VODB_BF16: return split_dispatch_dst<__nv_bfloat16>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, st);
+    case VODB_F16: return split_dispatch_dst<__half>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, st);
+  }
+  set_error("bad src dtype %d", src_dtype);
+  return VODB_EINVAL;
+}
+
 int launch_fill_synthetic(void* dst, int dtype, int dim, int pitch, uint64_t seed, int64_t global_row0, int64_t n,
                           int unit_norm, cudaStream_t st) {
   if (n == 0) return VODB_OK;
@@ -207,6 +255,9 @@ int launch_read_rows(const void* src, int dtype, int dim, int pitch, int64_t n, 
 }
 
 namespace {
+
+inline int mode_terms(int mode) { return mode == VODB_MODE_TENSOR_X3 ? 3 : mode == VODB_MODE_TENSOR_X2 ? 2 : 1; }
+inline bool is_tensor_mode(int mode) { return mode >= VODB_MODE_TENSOR && mode <= VODB_MODE_TENSOR_X3; }
 
 int pow2ceil_host(int64_t x) {
   int64_t p = 1;
@@ -249,7 +300,7 @@ int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes) {
   }
   // staged queries: rows padded to a multiple of 256 so that any TMA box is in bounds; zero filled
   size_t rows_pad = ((size_t)nq + 255) / 256 * 256;
-  size_t need = rows_pad * (size_t)s->pitch * 4;  // big enough for fp32 or 16-bit staging
+  size_t need = rows_pad * (size_t)s->pitch * 6;  // fp32 staging (4 B) or up to three 16-bit term planes (6 B)
   if (need > w.q_stage_bytes) {
     if (w.q_stage) cudaFree(w.q_stage);
     w.q_stage = nullptr;
@@ -340,9 +391,10 @@ int run_scan(vodb_store* s, const void* q_stage, int nq, int k, int mode, bool s
     a.overflow = w.overflow;
     a.cap = w.cap;
     a.dump = (i == 0);
+    a.terms = is_tensor_mode(mode) ? mode_terms(mode) : 1;
     ProfileState* prof = s->profiling ? static_cast<ProfileState*>(s->prof) : nullptr;
     if (prof) cudaEventRecord(prof->next(), st);
-    rc = (mode == VODB_MODE_TENSOR) ? launch_score_tensor(s, a, st) : launch_score_exact(a, s->sm_count, st);
+    rc = is_tensor_mode(mode) ? launch_score_tensor(s, a, st) : launch_score_exact(a, s->sm_count, st);
     if (rc != VODB_OK) return rc;
     if (prof) {
       cudaEventRecord(prof->next(), st);
@@ -351,8 +403,11 @@ int run_scan(vodb_store* s, const void* q_stage, int nq, int k, int mode, bool s
       cudaEventRecord(prof->next(), st);
     }
     bool last = (i + 2 == b.size());
+    // list length the select will see: the whole first segment (dump), afterwards k + ~k*g survivors (x2 slack)
+    const int expected_n = (i == 0) ? (int)(b[1] - b[0])
+                                    : (int)std::min<int64_t>(w.cap, 2 * (int64_t)k * (1 + (b[i + 1] - b[i]) / std::max<int64_t>(b[i], 1)) + 512);
     rc = launch_select(w.cand_s, w.cand_i, w.cnt, w.tau, w.cap, nq, k, last, out_s, out_i, s->row_offset, st,
-                       last ? xd : nullptr);
+                       last ? xd : nullptr, expected_n);
     if (rc != VODB_OK) return rc;
     if (prof) {
       cudaEventRecord(prof->next(), st);
@@ -399,10 +454,14 @@ int stage_queries(vodb_store* s, const void* queries, int q_dtype, int q_on_devi
     VODB_CUDA_CHECK(cudaMemcpyAsync(w.q_in, queries, (size_t)nq * s->dim * dtype_size(q_dtype), cudaMemcpyHostToDevice, st));
     q_dev = w.q_in;
   }
-  const int stage_dtype = (mode == VODB_MODE_TENSOR) ? s->dtype : VODB_F32;
   size_t rows_pad = ((size_t)nq + 255) / 256 * 256;
-  VODB_CUDA_CHECK(cudaMemsetAsync(w.q_stage, 0, rows_pad * s->pitch * dtype_size(stage_dtype), st));
-  return launch_convert_rows(q_dev, q_dtype, s->dim, w.q_stage, stage_dtype, s->pitch, nq, st);
+  if (mode == VODB_MODE_EXACT) {
+    VODB_CUDA_CHECK(cudaMemsetAsync(w.q_stage, 0, rows_pad * s->pitch * sizeof(float), st));
+    return launch_convert_rows(q_dev, q_dtype, s->dim, w.q_stage, VODB_F32, s->pitch, nq, st);
+  }
+  const int terms = mode_terms(mode);
+  VODB_CUDA_CHECK(cudaMemsetAsync(w.q_stage, 0, (size_t)terms * rows_pad * s->pitch * 2, st));
+  return launch_split_rows(q_dev, q_dtype, s->dim, w.q_stage, s->dtype, s->pitch, nq, (int64_t)rows_pad, terms, st);
 }
 
 int check_search_args(vodb_store* s, const void* queries, int q_dtype, int nq, int k, int mode, const float* out_scores,
@@ -412,7 +471,7 @@ int check_search_args(vodb_store* s, const void* queries, int q_dtype, int nq, i
   VODB_REQUIRE(nq >= 0, "%s: nq=%d < 0", fn, nq);
   VODB_REQUIRE(k >= 1 && k <= VODB_MAX_K, "%s: k=%d outside [1, %d]", fn, k, VODB_MAX_K);
   VODB_REQUIRE(q_dtype == VODB_F32 || q_dtype == VODB_BF16 || q_dtype == VODB_F16, "%s: bad query dtype %d", fn, q_dtype);
-  VODB_REQUIRE(mode == VODB_MODE_EXACT || mode == VODB_MODE_TENSOR, "%s: bad mode %d", fn, mode);
+  VODB_REQUIRE(mode == VODB_MODE_EXACT || is_tensor_mode(mode), "%s: bad mode %d", fn, mode);
   VODB_REQUIRE(nq == 0 || (out_scores != nullptr && out_idx != nullptr), "%s: output pointer is NULL", fn);
   return VODB_OK;
 }
@@ -578,8 +637,8 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
     set_error("vodb_search: the store is empty (faiss health check: 'ERROR: Index is empty')");
     return VODB_ESTATE;
   }
-  if (mode == VODB_MODE_TENSOR && !tensor_path_supported(s)) {
-    set_error("vodb_search: VODB_MODE_TENSOR needs a bf16/f16 store and a driver exporting cuTensorMapEncodeTiled");
+  if (is_tensor_mode(mode) && !tensor_path_supported(s)) {
+    set_error("vodb_search: VODB_MODE_TENSOR* needs a bf16/f16 store and a driver exporting cuTensorMapEncodeTiled");
     return VODB_EUNSUPPORTED;
   }
   DeviceGuard guard(s->device);
@@ -695,8 +754,8 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
   VODB_REQUIRE(x != nullptr && x->connected, "vodb_search_sharded: exchange is NULL or not connected");
   VODB_REQUIRE(x->device == s->device, "vodb_search_sharded: exchange and store live on different devices");
   VODB_REQUIRE(nq >= 1 && (size_t)nq * k <= x->slot, "vodb_search_sharded: nq*k=%lld exceeds the exchange slot (%zu)", (long long)nq * k, x->slot);
-  if (mode == VODB_MODE_TENSOR && !tensor_path_supported(s)) {
-    set_error("vodb_search_sharded: VODB_MODE_TENSOR needs a bf16/f16 store");
+  if (is_tensor_mode(mode) && !tensor_path_supported(s)) {
+    set_error("vodb_search_sharded: VODB_MODE_TENSOR* needs a bf16/f16 store");
     return VODB_EUNSUPPORTED;
   }
   DeviceGuard guard(s->device);

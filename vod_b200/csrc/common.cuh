@@ -134,6 +134,7 @@ struct SegmentArgs {
   const float* tau;
   int* overflow;
   int cap;
+  int terms;            // TENSOR: 16-bit terms per query (1..3), staged as [terms][round_up(nq,256)][pitch]
   bool dump;            // first segment of a scan: lists are empty, every score is stored at slot row-row_begin
 };
 
@@ -158,7 +159,7 @@ bool tensor_path_supported(const vodb_store* s);
 // select the k best candidates of every query list; if `final`, sort and write outputs
 int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap, int nq, int k, bool final,
                   float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream,
-                  const ExchangeDst* xd = nullptr);
+                  const ExchangeDst* xd = nullptr, int expected_n = 0);
 // merge of the gathered per-rank lists after waiting for every peer's epoch flag (see ExchangeDst)
 int launch_merge_exchange(const float* gather_s, const int64_t* gather_i, const uint32_t* flags, uint32_t epoch,
                           int world, size_t slot_elems, int nq, int k, float* out_s, int64_t* out_i,
@@ -169,6 +170,9 @@ int launch_init_lists(int* cnt, float* tau, int first_rows, int nq, cudaStream_t
 
 int launch_convert_rows(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch,
                         int64_t n, cudaStream_t stream);
+// queries -> `terms` planes of the 16-bit dtype: plane t holds round(q - sum of the previous planes)
+int launch_split_rows(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
+                      int64_t plane_rows, int terms, cudaStream_t stream);
 int launch_fill_synthetic(void* dst, int dtype, int dim, int pitch, uint64_t seed, int64_t global_row0, int64_t n,
                           int unit_norm, cudaStream_t stream);
 int launch_read_rows(const void* src, int dtype, int dim, int pitch, int64_t n, float* out, cudaStream_t stream);

@@ -134,6 +134,7 @@ struct TcParams {
   int nq;
   int n_ctiles, n_qtiles;
   int kchunks;  // pitch / KC
+  int q_rows_pad;  // rows of one query term plane in the staged query tensor [terms][q_rows_pad][pitch]
   float* cand_s;
   int32_t* cand_i;
   int* cnt;
@@ -223,11 +224,14 @@ __device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
   return (j & 16) ? d[1] : d[0];
 }
 
-template <int BN>
+// BN = queries per tile (MMA N); T = query terms: a float32 query is split into T 16-bit terms (hi, lo, lo2) whose
+// partial products accumulate into the same TMEM accumulator, so T=2 keeps ~16 and T=3 all 24 mantissa bits of
+// the query while the corpus tile is loaded from HBM/L2 only once per stage.
+template <int BN, int T>
 struct TcConfig {
   static constexpr uint32_t kABytes = BM * KC * 2;
-  static constexpr uint32_t kBBytes = BN * KC * 2;
-  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kBBytes = BN * KC * 2;          // one term
+  static constexpr uint32_t kStageBytes = kABytes + T * kBBytes;
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
   static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                         : (2 * BN <= 256) ? 256 : 512;
@@ -235,17 +239,17 @@ struct TcConfig {
                                          4 * BN * sizeof(float) /*tau, one copy per epilogue warp*/ + 4 * sizeof(WarpStage);
 };
 
-template <int BN>
+template <int BN, int T>
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_constant__ CUtensorMap tmap_query,
                 const TcParams p) {
-  using Cfg = TcConfig<BN>;
+  using Cfg = TcConfig<BN, T>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle (TMA writes and UMMA reads XOR address bits [4,7) with [7,10))
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_a = smem;                                   // STAGES x [128 x 128B]
-  unsigned char* smem_b = smem + STAGES * Cfg::kABytes;           // STAGES x [BN x 128B]
+  unsigned char* smem_b = smem + STAGES * Cfg::kABytes;           // STAGES x T x [BN x 128B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
@@ -299,7 +303,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC, row0, corpus_policy);
-          tma_load_2d(&tmap_query, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kc * KC, q0, kEvictLast);
+#pragma unroll
+          for (int t = 0; t < T; ++t)
+            tma_load_2d(&tmap_query, &full_bar[stage], smem_b + (stage * T + t) * Cfg::kBBytes, kc * KC,
+                        t * p.q_rows_pad + q0, kEvictLast);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -320,11 +327,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
           mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
           tcgen05_fence_after();
           const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t db = make_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
-          for (int k = 0; k < KC / UMMA_K; ++k) {
-            // advance 32 bytes (16 elements) inside the 128-byte swizzle atom: +2 in the >>4 address field
-            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kc | k) != 0 ? 1u : 0u);
+          for (int t = 0; t < T; ++t) {
+            const uint64_t db = make_desc_sw128(smem_u32(smem_b + (stage * T + t) * Cfg::kBBytes));
+#pragma unroll
+            for (int k = 0; k < KC / UMMA_K; ++k) {
+              // advance 32 bytes (16 elements) inside the 128-byte swizzle atom: +2 in the >>4 address field
+              umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kc | t | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once the MMAs above have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -489,12 +499,13 @@ int encode_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int p
   return VODB_OK;
 }
 
-template <int BN>
+template <int BN, int T>
 int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
-  using Cfg = TcConfig<BN>;
+  using Cfg = TcConfig<BN, T>;
+  static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
   static bool attr_set = false;
   if (!attr_set) {
-    VODB_CUDA_CHECK(cudaFuncSetAttribute(score_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VODB_CUDA_CHECK(cudaFuncSetAttribute(score_tc_kernel<BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -505,7 +516,8 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   }
   alignas(64) CUtensorMap tmap_q;
   // the staged query buffer is zero padded to a multiple of 256 rows (api.cu), so every BN-row box is in bounds
-  int rc = encode_2d(&tmap_q, a.queries, s->dtype, ((int64_t)a.nq + 255) / 256 * 256, s->pitch, BN);
+  const int64_t q_rows_pad = ((int64_t)a.nq + 255) / 256 * 256;
+  int rc = encode_2d(&tmap_q, a.queries, s->dtype, q_rows_pad * T, s->pitch, BN);
   if (rc != VODB_OK) return rc;
 
   TcParams p;
@@ -515,6 +527,7 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.n_ctiles = (int)((a.row_end - a.row_begin + BM - 1) / BM);
   p.n_qtiles = (a.nq + BN - 1) / BN;
   p.kchunks = s->pitch / KC;
+  p.q_rows_pad = (int)q_rows_pad;
   p.cand_s = a.cand_s;
   p.cand_i = a.cand_i;
   p.cnt = a.cnt;
@@ -527,7 +540,7 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
   if (items <= 0) return VODB_OK;
   int grid = (int)(items < s->sm_count ? items : s->sm_count);
-  score_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(*reinterpret_cast<CUtensorMap*>(s->tmap_corpus),
+  score_tc_kernel<BN, T><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(*reinterpret_cast<CUtensorMap*>(s->tmap_corpus),
                                                                    tmap_q, p);
   VODB_CUDA_CHECK(cudaGetLastError());
   return VODB_OK;
@@ -548,9 +561,20 @@ int launch_score_tensor(vodb_store* s, const SegmentArgs& a, cudaStream_t stream
     set_error("launch_score_tensor: shard too large for 32-bit TMA coordinates");
     return VODB_EUNSUPPORTED;
   }
-  if (a.nq <= 64) return launch_bn<64>(s, a, stream);
-  if (a.nq <= 128) return launch_bn<128>(s, a, stream);
-  return launch_bn<256>(s, a, stream);
+  switch (a.terms) {
+    case 1:
+      if (a.nq <= 64) return launch_bn<64, 1>(s, a, stream);
+      if (a.nq <= 128) return launch_bn<128, 1>(s, a, stream);
+      return launch_bn<256, 1>(s, a, stream);
+    case 2:
+      if (a.nq <= 64) return launch_bn<64, 2>(s, a, stream);
+      return launch_bn<128, 2>(s, a, stream);
+    case 3:
+      if (a.nq <= 64) return launch_bn<64, 3>(s, a, stream);
+      return launch_bn<128, 3>(s, a, stream);
+  }
+  set_error("launch_score_tensor: bad number of query terms %d", a.terms);
+  return VODB_EINVAL;
 }
 
 }  // namespace vodb

@@ -12,6 +12,8 @@
 //      them by (score desc, id asc) and writes scores / global ids, else they are written back to the
 //      front of the list and tau[q] := v* becomes the filter threshold of the next scan segment.
 // Exact (no approximation): the order is total because ids are unique within a list.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vodb {
@@ -81,29 +83,29 @@ __device__ __forceinline__ void find_bin(SelectSmem<IdxT>& sm, int need, int lan
   }
 }
 
-// Core routine. load(i, score, idx) reads entry i in [0,n). Results: sel_o/sel_i[0..n_sel) in shared
-// memory (sorted if do_sort), returns n_sel = min(n,k); *vstar_out = ord image of the k-th best score
-// (0 if n < k).
-template <typename IdxT, typename Loader>
-__device__ int block_select(Loader load, int n, int k, bool do_sort, SelectSmem<IdxT>& sm, uint32_t* sel_o,
-                            IdxT* sel_i, int P, uint32_t* vstar_out) {
+// Core routine. load_s(i) / load_i(i) read entry i in [0,n). Results: sel_o/sel_i[0..n_sel) in shared memory
+// (sorted if do_sort), returns n_sel = min(n,k); *vstar_out = ord image of the k-th best score (0 if n < k).
+// `cache` (optional, capacity cache_n >= n required to be used) keeps the ordered score images in shared memory
+// after the first pass, so that the remaining radix passes and the compaction never go back to L2.
+template <typename IdxT, typename LoadS, typename LoadI>
+__device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_sort, SelectSmem<IdxT>& sm,
+                            uint32_t* sel_o, IdxT* sel_i, int P, uint32_t* cache, int cache_n, uint32_t* vstar_out) {
   using U = typename UIdx<IdxT>::type;
   const int tid = threadIdx.x;
   const int nt = blockDim.x;
   int n_sel;
   uint32_t vstar = 0u;
+  const bool cached = cache != nullptr && n <= cache_n;
+  auto key = [&](int i) -> uint32_t { return cached ? cache[i] : ord_u32(load_s(i)); };
 
   if (n <= k) {
     if (tid == 0) sm.min_ord = 0xffffffffu;
     __syncthreads();
     uint32_t local_min = 0xffffffffu;
     for (int i = tid; i < n; i += nt) {
-      float s;
-      IdxT id;
-      load(i, s, id);
-      uint32_t o = ord_u32(s);
+      uint32_t o = ord_u32(load_s(i));
       sel_o[i] = o;
-      sel_i[i] = id;
+      sel_i[i] = load_i(i);
       local_min = min(local_min, o);
     }
     atomicMin(&sm.min_ord, local_min);
@@ -116,12 +118,26 @@ __device__ int block_select(Loader load, int n, int k, bool do_sort, SelectSmem<
     for (int shift = 24; shift >= 0; shift -= 8) {
       for (int t = tid; t < 256; t += nt) sm.hist[t] = 0;
       __syncthreads();
-      for (int i = tid; i < n; i += nt) {
-        float s;
-        IdxT id;
-        load(i, s, id);
-        uint32_t o = ord_u32(s);
-        if ((o & mask) == prefix) atomicAdd(&sm.hist[(o >> shift) & 255u], 1);
+      if (shift == 24) {
+        // first pass: read the scores from global memory (4 independent loads in flight per thread), fill the cache
+        int i = tid;
+        for (; i + 3 * nt < n; i += 4 * nt) {
+          float s0 = load_s(i), s1 = load_s(i + nt), s2 = load_s(i + 2 * nt), s3 = load_s(i + 3 * nt);
+          uint32_t o0 = ord_u32(s0), o1 = ord_u32(s1), o2 = ord_u32(s2), o3 = ord_u32(s3);
+          if (cached) { cache[i] = o0; cache[i + nt] = o1; cache[i + 2 * nt] = o2; cache[i + 3 * nt] = o3; }
+          atomicAdd(&sm.hist[o0 >> 24], 1); atomicAdd(&sm.hist[o1 >> 24], 1);
+          atomicAdd(&sm.hist[o2 >> 24], 1); atomicAdd(&sm.hist[o3 >> 24], 1);
+        }
+        for (; i < n; i += nt) {
+          uint32_t o = ord_u32(load_s(i));
+          if (cached) cache[i] = o;
+          atomicAdd(&sm.hist[o >> 24], 1);
+        }
+      } else {
+        for (int i = tid; i < n; i += nt) {
+          uint32_t o = key(i);
+          if ((o & mask) == prefix) atomicAdd(&sm.hist[(o >> shift) & 255u], 1);
+        }
       }
       __syncthreads();
       if (tid < 32) find_bin<true>(sm, need, tid);
@@ -143,10 +159,10 @@ __device__ int block_select(Loader load, int n, int k, bool do_sort, SelectSmem<
         for (int t = tid; t < 256; t += nt) sm.hist[t] = 0;
         __syncthreads();
         for (int i = tid; i < n; i += nt) {
-          float s;
-          IdxT id;
-          load(i, s, id);
-          if (ord_u32(s) == vstar && (((U)id) & imask) == iprefix) atomicAdd(&sm.hist[(int)((((U)id) >> shift) & 255u)], 1);
+          if (key(i) == vstar) {
+            U u = (U)load_i(i);
+            if ((u & imask) == iprefix) atomicAdd(&sm.hist[(int)((u >> shift) & 255u)], 1);
+          }
         }
         __syncthreads();
         if (tid < 32) find_bin<false>(sm, ineed, tid);
@@ -164,12 +180,11 @@ __device__ int block_select(Loader load, int n, int k, bool do_sort, SelectSmem<
     }
     __syncthreads();
     for (int i = tid; i < n; i += nt) {
-      float s;
-      IdxT id;
-      load(i, s, id);
-      uint32_t o = ord_u32(s);
+      uint32_t o = key(i);
+      if (o < vstar) continue;
+      IdxT id = load_i(i);
       bool take = o > vstar;
-      if (!take && o == vstar) {
+      if (!take) {
         U u = (U)id;
         if (u < istar) take = true;
         else if (u == istar) take = atomicAdd(&sm.dup_taken, 1) < ineed;
@@ -222,24 +237,23 @@ __host__ __device__ inline int pow2ceil(int x) {
 
 // dynamic smem layout: sel_o[P] | sel_i[P]
 template <typename IdxT>
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __launch_bounds__(1024)
 select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __restrict__ cnt, float* __restrict__ tau,
               int cap, int k, int P, int final_pass, float* __restrict__ out_s, int64_t* __restrict__ out_i,
-              int64_t row_offset, const ExchangeDst xd, int use_xd) {
+              int64_t row_offset, const ExchangeDst xd, int use_xd, int cache_n) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ SelectSmem<int32_t> sm;
   int32_t* sel_i = reinterpret_cast<int32_t*>(dyn);
   uint32_t* sel_o = reinterpret_cast<uint32_t*>(dyn + (size_t)P * sizeof(int32_t));
+  uint32_t* cache = cache_n > 0 ? sel_o + P : nullptr;
   const int q = blockIdx.x;
   const int n = min(cnt[q], cap);
   float* ls = cand_s + (size_t)q * cap;
   int32_t* li = cand_i + (size_t)q * cap;
-  auto load = [&](int i, float& s, int32_t& id) {
-    s = ls[i];
-    id = li[i];
-  };
+  auto load_s = [&](int i) -> float { return ls[i]; };
+  auto load_i = [&](int i) -> int32_t { return li[i]; };
   uint32_t vstar;
-  int n_sel = block_select<int32_t>(load, n, k, final_pass != 0, sm, sel_o, sel_i, P, &vstar);
+  int n_sel = block_select<int32_t>(load_s, load_i, n, k, final_pass != 0, sm, sel_o, sel_i, P, cache, cache_n, &vstar);
   __syncthreads();
   if (final_pass && use_xd) {
     // fused exchange: store this shard's result into every rank's gather buffer (own rank included)
@@ -293,14 +307,14 @@ merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, 
   uint32_t* sel_o = reinterpret_cast<uint32_t*>(dyn + (size_t)P * sizeof(int64_t));
   const int q = blockIdx.x;
   const int n = n_lists * k_in;
-  auto load = [&](int i, float& s, int64_t& id) {
+  auto off_of = [&](int i) -> size_t {
     int l = i / k_in, j = i - l * k_in;
-    size_t off = ((size_t)l * nq + q) * k_in + j;
-    s = scores[off];
-    id = idx[off];
+    return ((size_t)l * nq + q) * k_in + j;
   };
+  auto load_s = [&](int i) -> float { return scores[off_of(i)]; };
+  auto load_i = [&](int i) -> int64_t { return idx[off_of(i)]; };
   uint32_t vstar;
-  int n_sel = block_select<int64_t>(load, n, k_out, true, sm, sel_o, sel_i, P, &vstar);
+  int n_sel = block_select<int64_t>(load_s, load_i, n, k_out, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar);
   __syncthreads();
   for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
     bool ok = j < n_sel && sel_i[j] >= 0;
@@ -333,14 +347,14 @@ merge_exchange_kernel(const float* __restrict__ gather_s, const int64_t* __restr
   __syncthreads();
   const int q = blockIdx.x;
   const int n = world * k;
-  auto load = [&](int i, float& s, int64_t& id) {
+  auto off_of = [&](int i) -> size_t {
     int l = i / k, j = i - l * k;
-    size_t off = (size_t)l * slot_elems + (size_t)q * k + j;
-    s = gather_s[off];
-    id = gather_i[off];
+    return (size_t)l * slot_elems + (size_t)q * k + j;
   };
+  auto load_s = [&](int i) -> float { return gather_s[off_of(i)]; };
+  auto load_i = [&](int i) -> int64_t { return gather_i[off_of(i)]; };
   uint32_t vstar;
-  int n_sel = block_select<int64_t>(load, n, k, true, sm, sel_o, sel_i, P, &vstar);
+  int n_sel = block_select<int64_t>(load_s, load_i, n, k, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar);
   __syncthreads();
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     bool ok = j < n_sel && sel_i[j] >= 0;
@@ -369,13 +383,24 @@ int launch_init_lists(int* cnt, float* tau, int first_rows, int nq, cudaStream_t
 }
 
 int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap, int nq, int k, bool final_pass,
-                  float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream, const ExchangeDst* xd) {
+                  float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream, const ExchangeDst* xd,
+                  int expected_n) {
   int P = pow2ceil(k);
-  size_t smem = (size_t)P * (sizeof(int32_t) + sizeof(uint32_t));
+  // shared-memory cache of the ordered score images: sized for the list length the host expects (the first segment's
+  // row count, or a few multiples of k afterwards); longer lists fall back to re-reading L2 on every pass
+  int cache_n = std::min(std::max(expected_n, 0), std::min(cap, 32768));
+  cache_n = (cache_n + 255) / 256 * 256;
+  size_t smem = (size_t)P * (sizeof(int32_t) + sizeof(uint32_t)) + (size_t)cache_n * sizeof(uint32_t);
+  static size_t max_set = 48 * 1024;
+  if (smem > max_set) {
+    VODB_CUDA_CHECK(cudaFuncSetAttribute(select_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024)));
+    max_set = 160 * 1024;
+  }
   ExchangeDst none{};
-  select_kernel<int32_t><<<nq, kSelThreads, smem, stream>>>(cand_s, cand_i, cnt, tau, cap, k, P, final_pass ? 1 : 0,
-                                                            out_s, out_i, row_offset, xd ? *xd : none,
-                                                            (xd && final_pass) ? 1 : 0);
+  const int threads = (nq <= 512) ? 1024 : kSelThreads;  // few queries: more threads per list; many: more CTAs per SM
+  select_kernel<int32_t><<<nq, threads, smem, stream>>>(cand_s, cand_i, cnt, tau, cap, k, P, final_pass ? 1 : 0, out_s,
+                                                        out_i, row_offset, xd ? *xd : none,
+                                                        (xd && final_pass) ? 1 : 0, cache_n);
   VODB_CUDA_CHECK(cudaGetLastError());
   return VODB_OK;
 }

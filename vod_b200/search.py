@@ -194,12 +194,18 @@ class CorpusStore:
         return out
 
     # -- search
-    def _mode(self, mode: str | int | None) -> int:
+    def _mode(self, mode: str | int | None, q_code: int | None = None) -> int:
+        """Scoring mode. "auto": fp32 store -> fp32 CUDA-core kernel; 16-bit store -> tensor cores, with the query
+        kept exact: one term when the queries already are in the store dtype, else three 16-bit terms (full fp32
+        mantissa, IndexFlatIP parity at the fp32 tolerance). "tensor" forces one term (queries rounded)."""
         if mode is None or mode == "auto":
-            return _lib.MODE_EXACT if self.dtype_code == _lib.F32 else _lib.MODE_TENSOR
+            if self.dtype_code == _lib.F32:
+                return _lib.MODE_EXACT
+            return _lib.MODE_TENSOR if q_code == self.dtype_code else _lib.MODE_TENSOR_X3
         if isinstance(mode, int):
             return mode
-        return {"exact": _lib.MODE_EXACT, "fp32": _lib.MODE_EXACT, "tensor": _lib.MODE_TENSOR}[mode]
+        return {"exact": _lib.MODE_EXACT, "fp32": _lib.MODE_EXACT, "tensor": _lib.MODE_TENSOR,
+                "tensor2": _lib.MODE_TENSOR_X2, "tensor3": _lib.MODE_TENSOR_X3}[mode]
 
     def search(self, vectors: np.ndarray, top_k: int, mode: str | int | None = None) -> tuple[np.ndarray, np.ndarray]:
         """Host path: numpy [B, dim] in -> (scores f32 [B,k], ids i64 [B,k]); H2D / D2H inside the call."""
@@ -213,7 +219,7 @@ class CorpusStore:
         scores = np.empty((q.shape[0], top_k), np.float32)
         ids = np.empty((q.shape[0], top_k), np.int64)
         _lib.check(self._lib.vodb_search(self.handle, q.ctypes.data, _np_dtype_code(q), 0, q.shape[0], int(top_k),
-                                        self._mode(mode), scores.ctypes.data, ids.ctypes.data, 0,
+                                        self._mode(mode, _np_dtype_code(q)), scores.ctypes.data, ids.ctypes.data, 0,
                                         _current_stream_ptr(self.device)), "vodb_search")
         return scores, ids
 
@@ -232,7 +238,7 @@ class CorpusStore:
             ids = torch.empty((B, top_k), dtype=torch.int64, device=vectors.device)
         else:
             scores, ids = out
-        _lib.check(self._lib.vodb_search(self.handle, ptr, code, 1, B, int(top_k), self._mode(mode), scores.data_ptr(),
+        _lib.check(self._lib.vodb_search(self.handle, ptr, code, 1, B, int(top_k), self._mode(mode, code), scores.data_ptr(),
                                         ids.data_ptr(), 1, _current_stream_ptr(self.device)), "vodb_search")
         return scores, ids
 

@@ -159,7 +159,7 @@ class ShardedCorpus:
             scores, ids = out
         lib = _lib.load()
         _lib.check(lib.vodb_search_sharded(self.store.handle, self._xchg, ptr, code, 1, B, int(top_k),
-                                           self.store._mode(mode), int(safe), scores.data_ptr(), ids.data_ptr(), 1,
+                                           self.store._mode(mode, code), int(safe), scores.data_ptr(), ids.data_ptr(), 1,
                                            _current_stream_ptr(self.store.device)), "vodb_search_sharded")
         return scores, ids
 
