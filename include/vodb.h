@@ -160,6 +160,27 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
                         int k, int mode, int safe, float* out_scores, int64_t* out_idx, int out_on_device,
                         void* stream);
 
+/* ---- hybrid merge: normalise + weighted union + raw-score / label gather (the step between search and sampling) --
+ *
+ * Replaces, per query row, `_subtract_min_score` (src/vod_dataloaders/core/normalize.py:17-20), `result * weight`
+ * (src/vod_types/retrieval.py:222-233), the numba union `_nopy_merge_two_search_results` applied engine after
+ * engine (src/vod_dataloaders/core/merge.py:31-62, 108-164) and `gather_values_by_indices`
+ * (src/vod_dataloaders/core/numpy_ops.py:24-143) as `_merge_search_results` chains them (core/search.py:79-125).
+ *   scores[e]   [B, widths[e]] of score_dtype (VODB_F32, or 3 = float64), indices[e] int64 (negative = padding),
+ *   labels[e]   int64 or NULL; zero_scores[e] != 0 treats engine e's scores as 0 (the lookup engine)
+ *   normalize   subtract each engine's row minimum over finite scores, add `offset`
+ *   label_engine  engine whose labels are gathered into out_labels (-1: none; out_labels may be NULL)
+ *   outputs     out_scores/out_indices/out_labels [B, out_width], out_raw [n_engines, B, out_width] (NaN where the
+ *               engine did not return the id), out_counts[b] = number of distinct ids of row b. Slots past the
+ *               count hold id -1 / score -inf. The caller keeps columns [0, min(out_width, max_b count + 1)).
+ * Output order = first occurrence (engines in table order); duplicate ids are summed left to right, so results are
+ * bit-identical to the reference for equal dtypes. sum(widths) <= 8192. */
+int vodb_merge_results(int device, int n_engines, const void* const* scores, const int64_t* const* indices,
+                       const int64_t* const* labels, const int* widths, const double* weights,
+                       const int* zero_scores, int B, int score_dtype, int normalize, double offset,
+                       int label_engine, int out_width, void* out_scores, int64_t* out_indices,
+                       int64_t* out_labels, void* out_raw, int* out_counts, int on_device, void* stream);
+
 /* ---- labeled priority sampling ------------------------------------------ */
 
 /* Per row b of scores[B,K]: split entries by labels[b,:] > 0, priority-sample

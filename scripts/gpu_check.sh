@@ -19,6 +19,7 @@ if [[ $STEP == all || $STEP == tests ]]; then
   run t_search_exact 900 python -m pytest tests/test_search_gpu.py -q -m gpu --timeout=300 -k "exact or config1 or unit_norm or error or ingest or synthetic or client or row_offset" -p no:cacheprovider
   run t_search_tensor 900 python -m pytest tests/test_search_gpu.py -q -m gpu --timeout=300 -k "tensor or duplicate or adversarial or host_and_device" -p no:cacheprovider
   run t_sampling 900 python -m pytest tests/test_sampling_gpu.py -q -m gpu --timeout=300 -p no:cacheprovider
+  run t_merge 600 python -m pytest tests/test_merge_gpu.py -q -m gpu --timeout=300 -p no:cacheprovider
   run t_fullsize 1200 python -m pytest tests/test_fullsize_gpu.py -q -m gpu --timeout=600 -p no:cacheprovider
 fi
 if [[ $STEP == all || $STEP == bench ]]; then

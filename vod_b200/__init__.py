@@ -11,11 +11,14 @@ from .sampling import (PrioritySampledSections, labeled_priority_sampling, prior
                        sample_search_results)
 from .search import (B200SearchClient, B200SearchMaster, CorpusStore, DoNotPickleError, SearchClient,
                      build_b200_index, merge_topk, merge_topk_device)
+from .hybrid import async_hybrid_search, merge_search_results, normalize_search_scores_
+from .routing import ShardedSearchClient
 from .sharded import ShardedCorpus, ShardedSearcher, shard_bounds
 
 __all__ = [
     "B200SearchClient", "B200SearchMaster", "CorpusStore", "DoNotPickleError", "PrioritySampledSections",
-    "RetrievalBatch", "RetrievalSample", "RetrievalTuple", "SearchClient", "ShardedCorpus", "ShardedSearcher",
+    "RetrievalBatch", "RetrievalSample", "RetrievalTuple", "SearchClient", "ShardedCorpus", "ShardedSearchClient",
+    "ShardedSearcher", "async_hybrid_search", "merge_search_results", "normalize_search_scores_",
     "VodbError", "VodbUnavailableError", "build_b200_index", "labeled_priority_sampling", "merge_topk",
     "merge_topk_device", "priority_sampling_1d", "sample_search_results", "shard_bounds",
 ]

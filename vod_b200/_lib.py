@@ -55,6 +55,8 @@ _SIGNATURES = {
     "vodb_search_sharded": (_c.c_int, [_vp, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _vp,
                                        _vp, _c.c_int, _vp]),
     "vodb_merge_topk": (_c.c_int, [_c.c_int, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _vp, _vp, _c.c_int, _vp]),
+    "vodb_merge_results": (_c.c_int, [_c.c_int, _c.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _c.c_int, _c.c_int, _c.c_int,
+                                      _c.c_double, _c.c_int, _c.c_int, _vp, _vp, _vp, _vp, _vp, _c.c_int, _vp]),
     "vodb_sample": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float,
                                _c.c_int, _c.c_int, _c.c_uint64, _c.c_uint64, _vp, _vp, _vp, _vp, _c.c_int, _vp]),
 }

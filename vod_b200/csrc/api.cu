@@ -348,7 +348,10 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
   // number of survivors per query over the whole scan is ~ k*g*log_{1+g}(n/first), every survivor costs epilogue
   // time, and with thousands of queries that outweighs the fixed cost of a few more (select + launch) pairs.
   const bool large_batch = nq > 256;
-  int64_t first = round128(large_batch ? std::min(cap / 2, 4096) : cap / 2);
+  // first segment ("dump": every score stored, then one select): 16k rows is enough to give the first threshold
+  // (k-th best of the prefix) some bite; a longer prefix only makes the first select slower
+  int64_t first = round128(std::min<int64_t>(cap / 2, std::max<int64_t>(2048, 16LL * k)));
+  if (large_batch) first = std::min<int64_t>(first, std::max<int64_t>(4096, round128(4LL * k)));
   if (first >= n) {
     b.push_back(n);
     return b;
@@ -881,6 +884,87 @@ int vodb_merge_topk(int device, const float* scores, const int64_t* idx, int n_l
   cudaFree(d_s); cudaFree(d_i); cudaFree(d_os); cudaFree(d_oi);
   if (e != cudaSuccess) {
     set_error("vodb_merge_topk: %s", cudaGetErrorString(e));
+    return VODB_ECUDA;
+  }
+  return rc;
+}
+
+int vodb_merge_results(int device, int n_engines, const void* const* scores, const int64_t* const* indices,
+                       const int64_t* const* labels, const int* widths, const double* weights, const int* zero_scores,
+                       int B, int score_dtype, int normalize, double offset, int label_engine, int out_width,
+                       void* out_scores, int64_t* out_indices, int64_t* out_labels, void* out_raw, int* out_counts,
+                       int on_device, void* stream) {
+  VODB_REQUIRE(n_engines >= 1 && n_engines <= 8, "vodb_merge_results: n_engines=%d outside [1, 8]", n_engines);
+  VODB_REQUIRE(B >= 0 && out_width >= 1, "vodb_merge_results: bad B / out_width");
+  VODB_REQUIRE(score_dtype == VODB_F32 || score_dtype == 3 /* VODB_F64 */, "vodb_merge_results: score dtype must be f32 (0) or f64 (3)");
+  VODB_REQUIRE(scores && indices && widths && weights, "vodb_merge_results: NULL pointer table");
+  VODB_REQUIRE(label_engine >= -1 && label_engine < n_engines, "vodb_merge_results: bad label_engine");
+  VODB_REQUIRE(label_engine < 0 || (labels && labels[label_engine] && out_labels), "vodb_merge_results: label engine without labels");
+  if (B == 0) return VODB_OK;
+  VODB_REQUIRE(out_scores && out_indices && out_raw && out_counts, "vodb_merge_results: NULL output");
+  const int is_f64 = score_dtype != VODB_F32;
+  const size_t fsz = is_f64 ? 8 : 4;
+  int64_t M = 0;
+  for (int e = 0; e < n_engines; ++e) {
+    VODB_REQUIRE(widths[e] >= 0 && scores[e] && indices[e], "vodb_merge_results: engine %d has NULL arrays", e);
+    M += widths[e];
+  }
+  VODB_REQUIRE(M >= 1 && M <= 8192, "vodb_merge_results: %lld entries per row outside [1, 8192]", (long long)M);
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    set_error("cudaSetDevice(%d) failed", device);
+    return VODB_ECUDA;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (on_device)
+    return launch_merge_results(n_engines, scores, indices, labels, widths, weights, zero_scores, B, is_f64, normalize,
+                                offset, label_engine, out_width, out_scores, out_indices, out_labels, out_raw,
+                                out_counts, st);
+  // host buffers: one packed device allocation for inputs and outputs
+  size_t in_bytes = 0;
+  for (int e = 0; e < n_engines; ++e) in_bytes += (size_t)B * widths[e] * (fsz + 8 + 8);
+  const size_t nout = (size_t)B * out_width;
+  size_t out_bytes = nout * (fsz + 8 + 8) + (size_t)n_engines * nout * fsz + (size_t)B * 4 + 64;
+  char* d = nullptr;
+  VODB_CUDA_CHECK(cudaMalloc(&d, in_bytes + out_bytes + 256));
+  const void* d_scores[8];
+  const int64_t* d_idx[8];
+  const int64_t* d_lab[8];
+  char* cur = d;
+  cudaError_t e2 = cudaSuccess;
+  for (int e = 0; e < n_engines && e2 == cudaSuccess; ++e) {
+    size_t n = (size_t)B * widths[e];
+    d_idx[e] = reinterpret_cast<int64_t*>(cur);
+    e2 = cudaMemcpyAsync(cur, indices[e], n * 8, cudaMemcpyHostToDevice, st);
+    cur += n * 8;
+    d_lab[e] = nullptr;
+    if (e2 == cudaSuccess && labels && labels[e]) {
+      d_lab[e] = reinterpret_cast<int64_t*>(cur);
+      e2 = cudaMemcpyAsync(cur, labels[e], n * 8, cudaMemcpyHostToDevice, st);
+    }
+    cur += n * 8;
+    d_scores[e] = cur;
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(cur, scores[e], n * fsz, cudaMemcpyHostToDevice, st);
+    cur += (n * fsz + 7) / 8 * 8;
+  }
+  int64_t* o_i = reinterpret_cast<int64_t*>(cur); cur += nout * 8;
+  int64_t* o_l = reinterpret_cast<int64_t*>(cur); cur += nout * 8;
+  char* o_s = cur; cur += (nout * fsz + 7) / 8 * 8;
+  char* o_r = cur; cur += ((size_t)n_engines * nout * fsz + 7) / 8 * 8;
+  int* o_c = reinterpret_cast<int*>(cur);
+  int rc = VODB_OK;
+  if (e2 == cudaSuccess)
+    rc = launch_merge_results(n_engines, d_scores, d_idx, d_lab, widths, weights, zero_scores, B, is_f64, normalize,
+                              offset, label_engine, out_width, o_s, o_i, out_labels ? o_l : nullptr, o_r, o_c, st);
+  if (e2 == cudaSuccess && rc == VODB_OK) e2 = cudaMemcpyAsync(out_scores, o_s, nout * fsz, cudaMemcpyDeviceToHost, st);
+  if (e2 == cudaSuccess && rc == VODB_OK) e2 = cudaMemcpyAsync(out_indices, o_i, nout * 8, cudaMemcpyDeviceToHost, st);
+  if (e2 == cudaSuccess && rc == VODB_OK && out_labels) e2 = cudaMemcpyAsync(out_labels, o_l, nout * 8, cudaMemcpyDeviceToHost, st);
+  if (e2 == cudaSuccess && rc == VODB_OK) e2 = cudaMemcpyAsync(out_raw, o_r, (size_t)n_engines * nout * fsz, cudaMemcpyDeviceToHost, st);
+  if (e2 == cudaSuccess && rc == VODB_OK) e2 = cudaMemcpyAsync(out_counts, o_c, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
+  if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e2 != cudaSuccess) {
+    set_error("vodb_merge_results: %s", cudaGetErrorString(e2));
     return VODB_ECUDA;
   }
   return rc;

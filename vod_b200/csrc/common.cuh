@@ -177,6 +177,12 @@ int launch_fill_synthetic(void* dst, int dtype, int dim, int pitch, uint64_t see
                           int unit_norm, cudaStream_t stream);
 int launch_read_rows(const void* src, int dtype, int dim, int pitch, int64_t n, float* out, cudaStream_t stream);
 
+int launch_merge_results(int n_engines, const void* const* scores, const int64_t* const* indices,
+                         const int64_t* const* labels, const int* widths, const double* weights, const int* zero_scores,
+                         int B, int is_f64, int normalize, double offset, int label_engine, int out_width,
+                         void* out_scores, int64_t* out_indices, int64_t* out_labels, void* out_raw, int* out_counts,
+                         cudaStream_t stream);
+
 int launch_sample(const float* scores, const uint8_t* labels, const float* noise, int B, int K, int k_positive,
                   int k_total, int normalized, float temperature, int max_support, int quirks, uint64_t seed,
                   uint64_t offset, int64_t* out_ids, float* out_logw, uint8_t* out_labels, float* out_lse,

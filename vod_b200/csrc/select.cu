@@ -265,9 +265,11 @@ select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __r
         xd.peer_i[r][(size_t)q * k + j] = iv;
       }
     }
-    __threadfence_system();
+    // one system-scope fence per CTA: the barrier orders every thread's peer stores before thread 0's fence, which
+    // (cumulativity) makes them visible system-wide before the counter / flag updates that follow
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence_system();
       const int done = atomicAdd(xd.done_counter, 1);
       if (done == (int)gridDim.x - 1) {  // last CTA: every CTA's stores are fenced; publish the epoch on every peer
         *xd.done_counter = 0;
