@@ -47,7 +47,7 @@ def test_hybrid_merge_with_lookup_matches_oracle(dtype):
     """`_merge_search_results` (core/search.py:79-125): lookup scores zeroed, per-engine row-min subtraction, weighted
     union, raw scores / labels gathered — one kernel launch, compared with the oracle chain."""
     rng = np.random.default_rng(11)
-    B = 32
+    B = 4  # the oracle is a pure-Python O(B*K^2) loop
     res = {}
     for name, K in (("lookup", 8), ("dense", 1000), ("sparse", 1000)):
         idx = np.stack([rng.choice(5000, size=K, replace=False) for _ in range(B)]).astype(np.int64)
