@@ -8,6 +8,7 @@
 //   of the scores, and the [nq x rows] score matrix never exists in HBM. A list that runs out of room sets a
 //   device flag; the call then re-runs in "safe" mode (segments of cap-k rows, which cannot overflow).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -348,10 +349,15 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
   // number of survivors per query over the whole scan is ~ k*g*log_{1+g}(n/first), every survivor costs epilogue
   // time, and with thousands of queries that outweighs the fixed cost of a few more (select + launch) pairs.
   const bool large_batch = nq > 256;
-  // first segment ("dump": every score stored, then one select): 16k rows is enough to give the first threshold
-  // (k-th best of the prefix) some bite; a longer prefix only makes the first select slower
-  int64_t first = round128(std::min<int64_t>(cap / 2, std::max<int64_t>(2048, 16LL * k)));
+  // first segment ("dump": every score stored, then one select). Measured on B200 (scripts/sweep_schedule.py,
+  // 64 queries, k=100): 1024..8192 rows and growth 8..32 are within ~1% of each other on a 10M-row shard; on a
+  // 1.25M-row shard (8-GPU split) 4096/8192 rows with growth >= 20 (3 segments) beat 1024/2048 rows by ~7%.
+  int64_t first = round128(std::min<int64_t>(cap / 2, std::max<int64_t>(4096, 16LL * k)));
   if (large_batch) first = std::min<int64_t>(first, std::max<int64_t>(4096, round128(4LL * k)));
+  // tuning knobs (development): VODB_FIRST_ROWS / VODB_GROWTH override the schedule of small batches
+  static const char* env_first = std::getenv("VODB_FIRST_ROWS");
+  static const char* env_growth = std::getenv("VODB_GROWTH");
+  if (env_first && !large_batch) first = round128(std::min<int64_t>(cap / 2, std::max<int64_t>(2LL * k, std::atoll(env_first))));
   if (first >= n) {
     b.push_back(n);
     return b;
@@ -359,6 +365,7 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
   b.push_back(first);
   // growth: expected survivors of a segment = k * seg/before; keep that below cap/8
   double g = std::max(1.0, std::min((double)cap / (8.0 * k), large_batch ? 3.0 : 32.0));
+  if (env_growth && !large_batch) g = std::max(1.0, std::min(g, std::atof(env_growth)));
   int64_t cur = first;
   while (cur < n) {
     int64_t seg = round128((int64_t)(g * (double)cur));
