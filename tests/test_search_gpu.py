@@ -290,3 +290,35 @@ def test_multi_term_modes_bit_exact_on_integer_data(mode):
     rs, ri = flat_ip.search(xb, xq, 64)
     assert np.array_equal(i, ri) and np.array_equal(s, rs)
     st.close()
+
+
+def _remote_worker(blob, q):
+    import pickle
+
+    client = pickle.loads(blob)
+    rng = np.random.default_rng(9)
+    xq = int_valued(rng, (10, 48))
+    out = client.search(vector=xq, top_k=5)
+    q.put((client.ping(), out.scores, out.indices))
+
+
+@pytest.mark.timeout(180)
+def test_pickled_client_reaches_the_gpu_master_from_a_worker_process():
+    """DataLoader workers get pickled clients (reference: FaissClient(host, port) over HTTP); here they reach the
+    GPU-owning master over the Unix-socket transport and get the same bits as the in-process call."""
+    import multiprocessing as mp
+    import pickle
+
+    rng = np.random.default_rng(9)
+    vectors = int_valued(np.random.default_rng(1), (3000, 48))
+    xq = int_valued(rng, (10, 48))
+    with vod_b200.B200SearchMaster(vectors, dtype="bfloat16") as master:
+        client = master.get_client()
+        local = client.search(vector=xq, top_k=5)
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        p = ctx.Process(target=_remote_worker, args=(pickle.dumps(client), q))
+        p.start()
+        ok, s, i = q.get(timeout=150)
+        p.join(timeout=30)
+    assert ok and np.array_equal(s, local.scores) and np.array_equal(i, local.indices)

@@ -1,0 +1,64 @@
+"""The cross-process transport (Unix socket server thread + pickled client), with a numpy stand-in for the store so
+that it runs without a GPU: a spawned worker process unpickles the client and searches through the socket."""
+import multiprocessing as mp
+import pickle
+
+import numpy as np
+import pytest
+
+from vod_b200.search import B200SearchClient
+from vod_b200.transport import SearchServer
+
+
+def _fake_search(vectors, top_k, mode):
+    s = np.tile(vectors.sum(axis=1, keepdims=True), (1, top_k)).astype(np.float32) - np.arange(top_k, dtype=np.float32)
+    i = np.tile(np.arange(top_k, dtype=np.int64), (len(vectors), 1)) + (7 if mode == "exact" else 0)
+    if vectors.shape[1] == 3:
+        raise ValueError("query dimension 3 != index dimension 8")
+    return s, i
+
+
+def _worker(blob, q):
+    client = pickle.loads(blob)
+    out = client.search(vector=np.ones((4, 8), np.float32), top_k=5)
+    ok_ping = client.ping()
+    try:
+        client.search(vector=np.ones((1, 3), np.float32), top_k=2)
+        err = ""
+    except RuntimeError as exc:
+        err = str(exc)
+    q.put((out.scores, out.indices, type(out).__name__, ok_ping, err, out.scores.flags.writeable))
+
+
+@pytest.mark.timeout(120)
+def test_pickled_client_searches_from_another_process():
+    server = SearchServer(_fake_search, lambda: True)
+    server.start()
+    try:
+        client = B200SearchClient(master_id=12345, mode="exact", address=server.address, authkey=server.authkey)
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        p = ctx.Process(target=_worker, args=(pickle.dumps(client), q))
+        p.start()
+        scores, indices, cls_name, ok_ping, err, writable = q.get(timeout=100)
+        p.join(timeout=30)
+        assert p.exitcode == 0
+        exp_s, exp_i = _fake_search(np.ones((4, 8), np.float32), 5, "exact")
+        assert np.array_equal(scores, exp_s) and np.array_equal(indices, exp_i)
+        assert cls_name == "RetrievalBatch" and ok_ping and writable
+        assert "query dimension 3" in err           # server-side errors travel back to the caller
+    finally:
+        server.stop()
+    assert not B200SearchClient(1, pid=-1, address=server.address, authkey=server.authkey).ping()
+
+
+def test_client_without_master_or_address_fails_loudly():
+    import vod_b200
+
+    c = B200SearchClient(master_id=999)
+    assert c.ping() is False
+    with pytest.raises(vod_b200.VodbError):
+        c.search(vector=np.zeros((1, 8), np.float32), top_k=3)
+    c2 = pickle.loads(pickle.dumps(B200SearchClient(master_id=999, pid=-1)))
+    with pytest.raises(vod_b200.VodbError):
+        c2.search(vector=np.zeros((1, 8), np.float32), top_k=3)

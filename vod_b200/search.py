@@ -304,36 +304,58 @@ _master_ids = itertools.count(1)
 class B200SearchClient(SearchClient):
     """Drop-in for `FaissClient` (client.py:18-105): `search(vector=[B,D] float32, top_k)` -> RetrievalBatch.
 
-    The client is a light handle onto the master that owns the GPU state in this process. It pickles as
-    (master id, pid) like `FaissClient` pickles as (host, port); a handle unpickled in another process cannot
-    reach the GPU until the shared-memory transport exists and says so on first use.
+    The client is a light handle onto the master that owns the GPU state. In the master's process it calls the
+    store directly; pickled into another process (DataLoader workers, like `FaissClient(host, port)`) it reaches
+    the master through the Unix-socket transport of `vod_b200.transport` (address + auth key travel in the pickle).
     """
 
     requires_vectors: bool = True
 
-    def __init__(self, master_id: int, pid: int | None = None, mode: str | None = None):
+    def __init__(self, master_id: int, pid: int | None = None, mode: str | None = None,
+                 address: str | None = None, authkey: bytes | None = None):
         self.master_id = master_id
         self.pid = os.getpid() if pid is None else pid
         self.mode = mode
+        self.address = address
+        self.authkey = authkey
+        self._remote = None
 
     def __repr__(self) -> str:
         return f"{type(self).__name__}[master={self.master_id}](requires_vectors={self.requires_vectors})"
 
-    def _master(self) -> "B200SearchMaster":
-        if self.pid != os.getpid() or self.master_id not in _MASTERS:
+    def __getstate__(self) -> dict:
+        return {"master_id": self.master_id, "pid": self.pid, "mode": self.mode, "address": self.address,
+                "authkey": self.authkey}
+
+    def __setstate__(self, state: dict) -> None:
+        self.__dict__.update(state)
+        self._remote = None
+
+    def _local_master(self) -> "B200SearchMaster | None":
+        if self.pid == os.getpid():
+            return _MASTERS.get(self.master_id)
+        return None
+
+    def _remote_search(self):
+        if self.address is None or self.authkey is None:
             raise _lib.VodbError(
-                "this B200SearchClient was created in another process; the GPU-owning B200SearchMaster must live in "
-                "the calling process (cross-process transport is not implemented)."
+                "this B200SearchClient has no live master in this process and no transport address: enter the "
+                "B200SearchMaster (`with master:`) before handing clients to other processes."
             )
-        return _MASTERS[self.master_id]
+        if self._remote is None:
+            from .transport import RemoteSearch
+
+            self._remote = RemoteSearch(self.address, self.authkey)
+        return self._remote
 
     def ping(self, timeout: float = 120) -> bool:  # noqa: ARG002
         """True when the index is loaded and non-empty (server.py:59-66 health check)."""
-        try:
-            m = self._master()
-        except _lib.VodbError:
+        m = self._local_master()
+        if m is not None:
+            return m.store is not None and m.store.ntotal > 0
+        if self.pid == os.getpid() or self.address is None:
             return False
-        return m.store is not None and m.store.ntotal > 0
+        return self._remote_search().ping()
 
     def search(self, *, vector: np.ndarray, text: None | list[str] = None,  # noqa: ARG002
                subset_ids: None | list[list[SubsetId]] = None,  # noqa: ARG002
@@ -343,10 +365,18 @@ class B200SearchClient(SearchClient):
         """Search the index given a batch of vectors. `text`, `subset_ids`, `ids`, `shard` are accepted and
         ignored exactly like the faiss client does (client.py:68-71)."""
         start_time = time.time()
-        m = self._master()
-        if m.store is None:
-            raise _lib.VodbError("the master has not been entered (`with master as m:`)")
-        scores, indices = m.store.search(vector, top_k, mode=self.mode or m.mode)
+        m = self._local_master()
+        if m is not None:
+            if m.store is None:
+                raise _lib.VodbError("the master has not been entered (`with master as m:`)")
+            scores, indices = m.store.search(vector, top_k, mode=self.mode or m.mode)
+        elif self.pid == os.getpid():
+            raise _lib.VodbError("the B200SearchMaster of this client is not active (`with master as m:`)")
+        else:
+            q = np.ascontiguousarray(vector)
+            if q.ndim != 2:
+                raise ValueError(f"Expected 2D array, got {q.ndim}D array")  # server.py:82-83
+            scores, indices = self._remote_search().search(q, top_k, self.mode)
         return _retrieval_batch_cls().cast(indices=indices, scores=scores, labels=None,
                                            meta={"time": time.time() - start_time})
 
@@ -364,7 +394,7 @@ class B200SearchMaster:
 
     def __init__(self, vectors: typ.Any = None, *, dtype: str = "float32", device: int = 0, mode: str | None = None,
                  row_offset: int = 0, add_batch_size: int = 1 << 18, skip_setup: bool = False,
-                 free_resources: bool = False, store: CorpusStore | None = None):
+                 free_resources: bool = False, store: CorpusStore | None = None, serve: bool = True):
         self.vectors = vectors
         self.dtype = dtype
         self.device = device
@@ -376,16 +406,27 @@ class B200SearchMaster:
         self.store: CorpusStore | None = store
         self._owns_store = store is None
         self.master_id = next(_master_ids)
+        self.serve = serve  # expose the store to other processes (DataLoader workers) over a Unix socket
+        self._server = None
 
     # -- context manager (base.py:100-116)
     def __enter__(self) -> "B200SearchMaster":
         if not self.skip_setup:
             self._setup()
         _MASTERS[self.master_id] = self
+        if self.serve and self.store is not None:
+            from .transport import SearchServer
+
+            self._server = SearchServer(lambda v, k, mode: self.store.search(v, k, mode=mode or self.mode),
+                                        lambda: self.store is not None and self.store.ntotal > 0)
+            self._server.start()
         return self
 
     def __exit__(self, exc_type, exc_val, exc_tb) -> None:  # noqa: ANN001
         _MASTERS.pop(self.master_id, None)
+        if self._server is not None:
+            self._server.stop()
+            self._server = None
         if self.store is not None and self._owns_store:
             self.store.close()
             self.store = None
@@ -399,7 +440,9 @@ class B200SearchMaster:
                                       add_batch_size=self.add_batch_size)
 
     def get_client(self) -> B200SearchClient:
-        return B200SearchClient(self.master_id, mode=self.mode)
+        srv = self._server
+        return B200SearchClient(self.master_id, mode=self.mode, address=srv.address if srv else None,
+                                authkey=srv.authkey if srv else None)
 
     @property
     def service_name(self) -> str:
