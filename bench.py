@@ -63,6 +63,15 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def traffic_bytes(algorithmic_bytes: float):
+    """DRAM bytes per search = algorithmic bytes x the traffic ratio measured by `ncu --set full`
+    (dram__bytes_read.sum + dram__bytes_write.sum over the scoring launches, profiles/traffic.json)."""
+    path = ROOT / "profiles" / "traffic.json"
+    if not path.exists():
+        return None
+    return algorithmic_bytes * json.loads(path.read_text())["score_tc64_dram_over_algorithmic"]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
 
@@ -257,7 +266,7 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": "score_tc_kernel<64> (tcgen05 + TMA, fused top-k filter)",
         "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
-        "traffic": None, "peak_source": peaks["source"],
+        "traffic": traffic_bytes(shard_bytes), "peak_source": peaks["source"],
         "algorithmic_bytes_per_search_per_gpu": shard_bytes, "score_kernel_ms_per_search": score_ms_per_search,
         "select_kernel_ms_per_search": prof["select_ms"] / args.steps, "score_launches_per_search": prof["score_launches"] / args.steps,
         "whole_step_frac": (shard_bytes / (ms_step * 1e-3) / 1e9) / peaks["hbm_gbs"],
@@ -290,6 +299,49 @@ def main():
            "d2h_bytes_per_step": Q_SMALL * TOP_K * 12, "ms_per_step": e2e_s / args.steps * 1e3,
            "api": "B200SearchClient.search(vector=np.ndarray[64,768] f32) -> RetrievalBatch" if world == 1
            else "ShardedCorpus.search_device on pinned host queries + .cpu() of the merged result"}
+
+    # ---- per-call latency (search enqueue -> results ready on the device), p10 / p50 / p90 over fresh batches ----
+    lat_q = make_queries(torch, 40, Q_SMALL, dev, torch.bfloat16)
+    lat = []
+    for i in range(40):
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        corpus.search_device(lat_q[i], TOP_K, mode="tensor")
+        a1.record()
+        torch.cuda.synchronize()
+        if i >= 8:
+            lat.append(max_over_ranks(a0.elapsed_time(a1)))
+    lat.sort()
+    latency = {"unit": "ms", "p10": lat[len(lat) // 10], "p50": lat[len(lat) // 2], "p90": lat[(len(lat) * 9) // 10],
+               "n": len(lat), "what": "one 64-query search, device-resident in and out, CUDA events, max over ranks"}
+
+    # ---- BASELINE configs[3]: RealmCollate-style chain, 32 queries -> top-1000 -> priority sampling of 8 (rank 0) ----
+    config4 = None
+    if world == 1:
+        try:
+            pipe = vod_b200.DenseRetrievalSampler(corpus.store, top_k=1000, total=8, max_pos_sections=3, mode="tensor")
+            q4 = make_queries(torch, 30, 32, "cpu", torch.bfloat16).pin_memory()
+            times, samp = [], []
+            for i in range(30):
+                t0 = time.perf_counter()
+                pipe(q4[i], seed=42, offset=i)
+                times.append((time.perf_counter() - t0) * 1e3)
+            sc4 = torch.randn((32, 1000), device=dev)
+            for i in range(30):
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record()
+                vod_b200.sample_device(sc4, None, k_positive=3, k_total=8, seed=42, offset=i)
+                b1.record()
+                torch.cuda.synchronize()
+                samp.append(b0.elapsed_time(b1) * 1e3)
+            times, samp = sorted(times[5:]), sorted(samp[5:])
+            config4 = {"workload": "32 queries -> exact top-1000 over the 10M x 768 bf16 shard -> labeled priority sampling of 8 "
+                                   "(host queries in, [32,8] picks + log-weights out, one D2H)",
+                       "chain_ms_p50": times[len(times) // 2], "chain_ms_p90": times[(len(times) * 9) // 10],
+                       "sampler_kernel_us_p50": samp[len(samp) // 2]}
+        except Exception as exc:
+            config4 = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- large-batch (tensor-core regime) section ----
     large = None
@@ -342,7 +394,7 @@ def main():
             "corpus_gb_per_s": args.rows * DIM * 2 / (ms_step * 1e-3) / 1e9,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step, "segments": int(stats["segments"]), "cap": int(stats["cap"]),
-            "clocks": clocks, "large_batch": large,
+            "clocks": clocks, "latency": latency, "config4_retrieve_and_sample": config4, "large_batch": large,
         }
         print(json.dumps(line))
     if world > 1:

@@ -180,3 +180,28 @@ def test_labeled_priority_sampling_unbiased(seed, label_thres, n_trials=3000, n=
         assert np.isclose(mu_a, np.mean(mu_a_hats), atol=10.0 / np.sqrt(n_trials * min(k_positive, np.sum(labels == 1))))
     if mu_b is not None:
         assert np.isclose(mu_b, np.mean(mu_b_hats), atol=10.0 / np.sqrt(n_trials * min(k_total - k_positive, np.sum(labels == 0))))
+
+
+def test_device_resident_retrieve_then_sample_equals_host_path():
+    """Config 4 chain (32 queries, top-K=1000, sample 8): the device-resident pipeline returns the same picks and
+    weights as search -> numpy -> sample_search_results, with a single [B,8] device->host transfer."""
+    from tests.helpers import int_valued
+
+    rng = np.random.default_rng(2)
+    n, d, B = 50_000, 128, 32
+    st = vod_b200.CorpusStore(n, d, dtype="bfloat16")
+    st.add(int_valued(rng, (n, d)))
+    xq = int_valued(rng, (B, d))
+    s, i = st.search(xq, 1000, mode="tensor")
+    gold = np.stack([i[b, rng.choice(50, size=2, replace=False)] for b in range(B)])  # two retrieved ids per row are "gold"
+    labels = (i[:, :, None] == gold[:, None, :]).any(-1).astype(np.int64)
+    host = vod_b200.sample_search_results(search_results=vod_b200.RetrievalBatch(scores=s, indices=i, labels=labels),
+                                          raw_scores={"dense": s}, total=8, max_pos_sections=3, seed=5, offset=2)
+    pipe = vod_b200.DenseRetrievalSampler(st, top_k=1000, total=8, max_pos_sections=3, mode="tensor")
+    dev = pipe(xq, positive_ids=gold, seed=5, offset=2)
+    assert np.array_equal(dev.batch.indices, host.batch.indices)
+    assert np.array_equal(dev.batch.labels, host.batch.labels)
+    assert _same_bits(dev.log_weights, host.log_weights)
+    assert np.array_equal(dev.batch.scores, host.batch.scores)
+    assert dev.batch.labels[:, :2].all()
+    st.close()

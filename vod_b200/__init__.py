@@ -6,6 +6,7 @@ dataloader's labeled priority sampling, as hand-written CUDA (sm_100a) behind th
 """
 from . import _lib
 from ._lib import VodbError, VodbUnavailableError
+from .pipeline import DenseRetrievalSampler, sample_device
 from .retrieval import RetrievalBatch, RetrievalSample, RetrievalTuple
 from .sampling import (PrioritySampledSections, labeled_priority_sampling, priority_sampling_1d,
                        sample_search_results)
@@ -16,7 +17,7 @@ from .routing import ShardedSearchClient
 from .sharded import ShardedCorpus, ShardedSearcher, shard_bounds
 
 __all__ = [
-    "B200SearchClient", "B200SearchMaster", "CorpusStore", "DoNotPickleError", "PrioritySampledSections",
+    "B200SearchClient", "B200SearchMaster", "CorpusStore", "DenseRetrievalSampler", "sample_device", "DoNotPickleError", "PrioritySampledSections",
     "RetrievalBatch", "RetrievalSample", "RetrievalTuple", "SearchClient", "ShardedCorpus", "ShardedSearchClient",
     "ShardedSearcher", "async_hybrid_search", "merge_search_results", "normalize_search_scores_",
     "VodbError", "VodbUnavailableError", "build_b200_index", "labeled_priority_sampling", "merge_topk",
