@@ -16,8 +16,7 @@ run() { # name timeout cmd...
 echo "##### $(date) step=$STEP" >> gpurun_out/summary.txt
 if [[ $STEP == all || $STEP == tests ]]; then
   run smoke 300 python __graft_entry__.py --smoke
-  run t_search_exact 900 python -m pytest tests/test_search_gpu.py -q -m gpu --timeout=300 -k "exact or config1 or unit_norm or error or ingest or synthetic or client or row_offset" -p no:cacheprovider
-  run t_search_tensor 900 python -m pytest tests/test_search_gpu.py -q -m gpu --timeout=300 -k "tensor or duplicate or adversarial or host_and_device" -p no:cacheprovider
+  run t_search 900 python -m pytest tests/test_search_gpu.py -q -m gpu --timeout=300 -p no:cacheprovider
   run t_sampling 900 python -m pytest tests/test_sampling_gpu.py -q -m gpu --timeout=300 -p no:cacheprovider
   run t_merge 600 python -m pytest tests/test_merge_gpu.py -q -m gpu --timeout=300 -p no:cacheprovider
   run t_fullsize 1200 python -m pytest tests/test_fullsize_gpu.py -q -m gpu --timeout=600 -p no:cacheprovider
@@ -30,5 +29,9 @@ if [[ $STEP == all || $STEP == ncu ]]; then
   run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --large-steps 1
   run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:score_tc -s 4 -c 4 -o gpurun_out/prof_score_tc python bench.py --steps 2 --warmup 1 --no-cpu --no-large
   run ncu_full256 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'score_tc_kernel<.int.256>' -s 4 -c 4 -o gpurun_out/prof_score_tc256 python bench.py --steps 1 --warmup 1 --no-cpu --large-steps 1
+fi
+if [[ $STEP == all || $STEP == sanitizer ]]; then
+  run sanitizer_memcheck 600 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitizer_probe.py
+  run sanitizer_racecheck 600 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/sanitizer_probe.py small
 fi
 echo "=== done" | tee -a gpurun_out/summary.txt

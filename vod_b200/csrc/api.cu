@@ -279,21 +279,26 @@ int choose_cap(int nq, int k) {
 int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes) {
   Workspace& w = s->ws;
   int cap = choose_cap(nq, k);
-  if (nq > w.nq_cap || cap > w.cap) {
+  // lists are laid out [nq, cap] with the cap of THIS call as row stride (a larger stride left over from an earlier
+  // call with another k would only spread the lists over more cache lines)
+  const size_t need_elems = (size_t)nq * cap;
+  if (need_elems > w.list_elems) {
     if (w.cand_s) cudaFree(w.cand_s);
     if (w.cand_i) cudaFree(w.cand_i);
+    w.cand_s = nullptr; w.cand_i = nullptr;
+    VODB_CUDA_CHECK(cudaMalloc(&w.cand_s, need_elems * sizeof(float)));
+    VODB_CUDA_CHECK(cudaMalloc(&w.cand_i, need_elems * sizeof(int32_t)));
+    w.list_elems = need_elems;
+  }
+  if (nq > w.nq_cap) {
     if (w.cnt) cudaFree(w.cnt);
     if (w.tau) cudaFree(w.tau);
-    w.cand_s = nullptr; w.cand_i = nullptr; w.cnt = nullptr; w.tau = nullptr;
-    int nq_cap = std::max(nq, w.nq_cap);
-    int ncap = std::max(cap, w.cap);
-    VODB_CUDA_CHECK(cudaMalloc(&w.cand_s, (size_t)nq_cap * ncap * sizeof(float)));
-    VODB_CUDA_CHECK(cudaMalloc(&w.cand_i, (size_t)nq_cap * ncap * sizeof(int32_t)));
-    VODB_CUDA_CHECK(cudaMalloc(&w.cnt, (size_t)nq_cap * sizeof(int)));
-    VODB_CUDA_CHECK(cudaMalloc(&w.tau, (size_t)nq_cap * sizeof(float)));
-    w.nq_cap = nq_cap;
-    w.cap = ncap;
+    w.cnt = nullptr; w.tau = nullptr;
+    VODB_CUDA_CHECK(cudaMalloc(&w.cnt, (size_t)nq * sizeof(int)));
+    VODB_CUDA_CHECK(cudaMalloc(&w.tau, (size_t)nq * sizeof(float)));
+    w.nq_cap = nq;
   }
+  w.cap = cap;
   if (!w.overflow) {
     VODB_CUDA_CHECK(cudaMalloc(&w.overflow, sizeof(int)));
     VODB_CUDA_CHECK(cudaMemset(w.overflow, 0, sizeof(int)));
@@ -666,11 +671,15 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
     // with vodb_search_check() (bench / pipelined callers) and re-runs synchronously if it fired.
     return run_scan(s, w.q_stage, nq, k, mode, /*safe=*/false, o_s, o_i, st);
   }
+  // host outputs: results and the overflow flag come back with ONE synchronisation; if a list overflowed (rare)
+  // the batch is re-run on the overflow-proof schedule and copied again
   bool safe = false;
   for (int attempt = 0; attempt < 2; ++attempt) {
     rc = run_scan(s, w.q_stage, nq, k, mode, safe, o_s, o_i, st);
     if (rc != VODB_OK) return rc;
     VODB_CUDA_CHECK(cudaMemcpyAsync(w.overflow_host, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VODB_CUDA_CHECK(cudaMemcpyAsync(out_scores, w.out_s, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    VODB_CUDA_CHECK(cudaMemcpyAsync(out_idx, w.out_i, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     VODB_CUDA_CHECK(cudaStreamSynchronize(st));
     if (*w.overflow_host == 0) break;
     VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
@@ -679,11 +688,6 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
       return VODB_ESTATE;
     }
     safe = true;  // re-run with segments that cannot overflow
-  }
-  if (!out_on_device) {
-    VODB_CUDA_CHECK(cudaMemcpyAsync(out_scores, w.out_s, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-    VODB_CUDA_CHECK(cudaMemcpyAsync(out_idx, w.out_i, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    VODB_CUDA_CHECK(cudaStreamSynchronize(st));
   }
   return VODB_OK;
 }

@@ -81,8 +81,9 @@ struct Workspace {
   float* tau = nullptr;
   int* overflow = nullptr;     // device flag: a candidate list ran out of room
   int* overflow_host = nullptr;  // pinned mirror
-  int nq_cap = 0;
-  int cap = 0;
+  int nq_cap = 0;        // counters / thresholds allocated for this many queries
+  size_t list_elems = 0; // candidate slots allocated in total (>= nq * cap of the current call)
+  int cap = 0;           // per-query list capacity (= row stride) of the current call
   // staged queries (converted / padded) and staged outputs for host callers
   void* q_stage = nullptr;
   size_t q_stage_bytes = 0;
