@@ -100,6 +100,31 @@ __global__ void split_rows_kernel(const S* __restrict__ src, int src_dim, D* __r
   }
 }
 
+// prepare = query staging + list reset. dst dtype float: one plane (EXACT mode); 16-bit: `terms` planes.
+template <typename S, typename D>
+__global__ void prepare_kernel(const S* __restrict__ src, int src_dim, D* __restrict__ dst, int dst_pitch, int64_t n,
+                               int64_t plane_rows, int terms, int* __restrict__ cnt, float* __restrict__ tau,
+                               int first_rows) {
+  pdl_launch_dependents();
+  pdl_wait();  // the previous search on this stream may still be reading the staging buffer / lists
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gtid < n) {
+    cnt[gtid] = first_rows;
+    tau[gtid] = -INFINITY;
+  }
+  int64_t total = n * dst_pitch;
+  for (int64_t e = gtid; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = e / dst_pitch;
+    int c = (int)(e - r * dst_pitch);
+    float v = (c < src_dim) ? to_f32<S>(src[r * src_dim + c]) : 0.0f;
+    for (int t = 0; t < terms; ++t) {
+      D d = from_f32<D>(v);
+      dst[(size_t)t * plane_rows * dst_pitch + e] = d;
+      v = __fsub_rn(v, to_f32<D>(d));
+    }
+  }
+}
+
 template <typename D>
 __device__ __forceinline__ D round_store(float v);
 template <>
@@ -222,6 +247,37 @@ int launch_split_rows(const void* src, int src_dtype, int src_dim, void* dst, in
   return VODB_EINVAL;
 }
 
+namespace {
+template <typename S>
+int prepare_dispatch_dst(const void* src, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
+                         int64_t plane_rows, int terms, int* cnt, float* tau, int first_rows, cudaStream_t st) {
+  int64_t total = n * dst_pitch;
+  if (total == 0) return VODB_OK;
+  int g = std::max(grid_for(total), (int)((n + 255) / 256));  // every query needs a thread for the list reset
+  const S* s = reinterpret_cast<const S*>(src);
+  cudaError_t e;
+  switch (dst_dtype) {
+    case VODB_F32: e = launch_pdl(prepare_kernel<S, float>, dim3(g), dim3(256), 0, st, s, src_dim, (float*)dst, dst_pitch, n, plane_rows, 1, cnt, tau, first_rows); break;
+    case VODB_BF16: e = launch_pdl(prepare_kernel<S, __nv_bfloat16>, dim3(g), dim3(256), 0, st, s, src_dim, (__nv_bfloat16*)dst, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows); break;
+    case VODB_F16: e = launch_pdl(prepare_kernel<S, __half>, dim3(g), dim3(256), 0, st, s, src_dim, (__half*)dst, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows); break;
+    default: set_error("launch_prepare: bad destination dtype %d", dst_dtype); return VODB_EINVAL;
+  }
+  VODB_CUDA_CHECK(e);
+  return VODB_OK;
+}
+}  // namespace
+
+int launch_prepare(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
+                   int64_t plane_rows, int terms, int* cnt, float* tau, int first_rows, cudaStream_t st) {
+  switch (src_dtype) {
+    case VODB_F32: return prepare_dispatch_dst<float>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows, st);
+    case VODB_BF16: return prepare_dispatch_dst<__nv_bfloat16>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows, st);
+    case VODB_F16: return prepare_dispatch_dst<__half>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows, st);
+  }
+  set_error("bad src dtype %d", src_dtype);
+  return VODB_EINVAL;
+}
+
 int launch_fill_synthetic(void* dst, int dtype, int dim, int pitch, uint64_t seed, int64_t global_row0, int64_t n,
                           int unit_norm, cudaStream_t st) {
   if (n == 0) return VODB_OK;
@@ -311,6 +367,7 @@ int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes) {
     if (w.q_stage) cudaFree(w.q_stage);
     w.q_stage = nullptr;
     VODB_CUDA_CHECK(cudaMalloc(&w.q_stage, need));
+    VODB_CUDA_CHECK(cudaMemset(w.q_stage, 0, need));
     w.q_stage_bytes = need;
   }
   size_t need_in = (size_t)nq * s->dim * q_elem_bytes;
@@ -382,12 +439,17 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
   return b;
 }
 
-int run_scan(vodb_store* s, const void* q_stage, int nq, int k, int mode, bool safe, float* out_s, int64_t* out_i,
-             cudaStream_t st, const ExchangeDst* xd = nullptr) {
+int run_scan(vodb_store* s, const void* q_dev, int q_dtype, int nq, int k, int mode, bool safe, float* out_s,
+             int64_t* out_i, cudaStream_t st, const ExchangeDst* xd = nullptr) {
   Workspace& w = s->ws;
+  const void* q_stage = w.q_stage;
   std::vector<int64_t> b = plan_segments(s->n_added, w.cap, k, nq, safe);
-  // the first segment (<= cap/2 rows, or <= cap-k in safe mode) stores every score: lists start pre-sized
-  int rc = launch_init_lists(w.cnt, w.tau, (int)(b[1] - b[0]), nq, st);
+  // one launch stages the queries (fp32 plane, or `terms` 16-bit planes of round_up(nq,256) rows each) and resets the
+  // lists; the first segment (dump mode) stores every score, so cnt starts at its row count
+  const int64_t rows_pad = ((int64_t)nq + 255) / 256 * 256;
+  const bool tensor = is_tensor_mode(mode);
+  int rc = launch_prepare(q_dev, q_dtype, s->dim, w.q_stage, tensor ? s->dtype : VODB_F32, s->pitch, nq, rows_pad,
+                          tensor ? mode_terms(mode) : 1, w.cnt, w.tau, (int)(b[1] - b[0]), st);
   if (rc != VODB_OK) return rc;
   int64_t launches = 1;
   for (size_t i = 0; i + 1 < b.size(); ++i) {
@@ -461,22 +523,18 @@ struct vodb_xchg {
 };
 
 namespace {
-// convert / pad the query batch into the store's staging buffer (shared by vodb_search and vodb_search_sharded)
-int stage_queries(vodb_store* s, const void* queries, int q_dtype, int q_on_device, int nq, int mode, cudaStream_t st) {
+// host queries are copied to the device here; staging (convert / split / pad) happens in run_scan's prepare kernel.
+// Rows of the staging buffer past nq keep whatever an earlier call left there: their score columns are never read
+// (tau = +inf / q < nq guards in the scoring kernels).
+int upload_queries(vodb_store* s, const void* queries, int q_dtype, int q_on_device, int nq, cudaStream_t st,
+                   const void** q_dev) {
   Workspace& w = s->ws;
-  const void* q_dev = queries;
+  *q_dev = queries;
   if (!q_on_device) {
     VODB_CUDA_CHECK(cudaMemcpyAsync(w.q_in, queries, (size_t)nq * s->dim * dtype_size(q_dtype), cudaMemcpyHostToDevice, st));
-    q_dev = w.q_in;
+    *q_dev = w.q_in;
   }
-  size_t rows_pad = ((size_t)nq + 255) / 256 * 256;
-  if (mode == VODB_MODE_EXACT) {
-    VODB_CUDA_CHECK(cudaMemsetAsync(w.q_stage, 0, rows_pad * s->pitch * sizeof(float), st));
-    return launch_convert_rows(q_dev, q_dtype, s->dim, w.q_stage, VODB_F32, s->pitch, nq, st);
-  }
-  const int terms = mode_terms(mode);
-  VODB_CUDA_CHECK(cudaMemsetAsync(w.q_stage, 0, (size_t)terms * rows_pad * s->pitch * 2, st));
-  return launch_split_rows(q_dev, q_dtype, s->dim, w.q_stage, s->dtype, s->pitch, nq, (int64_t)rows_pad, terms, st);
+  return VODB_OK;
 }
 
 int check_search_args(vodb_store* s, const void* queries, int q_dtype, int nq, int k, int mode, const float* out_scores,
@@ -661,7 +719,8 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
   rc = ensure_workspace(s, nq, k, dtype_size(q_dtype));
   if (rc != VODB_OK) return rc;
   Workspace& w = s->ws;
-  rc = stage_queries(s, queries, q_dtype, q_on_device, nq, mode, st);
+  const void* q_dev = nullptr;
+  rc = upload_queries(s, queries, q_dtype, q_on_device, nq, st, &q_dev);
   if (rc != VODB_OK) return rc;
 
   float* o_s = out_on_device ? out_scores : w.out_s;
@@ -669,13 +728,13 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
   if (out_on_device) {
     // asynchronous: only enqueue. A list overflow leaves the sticky device flag set; the caller polls it
     // with vodb_search_check() (bench / pipelined callers) and re-runs synchronously if it fired.
-    return run_scan(s, w.q_stage, nq, k, mode, /*safe=*/false, o_s, o_i, st);
+    return run_scan(s, q_dev, q_dtype, nq, k, mode, /*safe=*/false, o_s, o_i, st);
   }
   // host outputs: results and the overflow flag come back with ONE synchronisation; if a list overflowed (rare)
   // the batch is re-run on the overflow-proof schedule and copied again
   bool safe = false;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    rc = run_scan(s, w.q_stage, nq, k, mode, safe, o_s, o_i, st);
+    rc = run_scan(s, q_dev, q_dtype, nq, k, mode, safe, o_s, o_i, st);
     if (rc != VODB_OK) return rc;
     VODB_CUDA_CHECK(cudaMemcpyAsync(w.overflow_host, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
     VODB_CUDA_CHECK(cudaMemcpyAsync(out_scores, w.out_s, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -777,7 +836,8 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
   rc = ensure_workspace(s, nq, k, dtype_size(q_dtype));
   if (rc != VODB_OK) return rc;
   Workspace& w = s->ws;
-  rc = stage_queries(s, queries, q_dtype, q_on_device, nq, mode, st);
+  const void* q_dev = nullptr;
+  rc = upload_queries(s, queries, q_dtype, q_on_device, nq, st, &q_dev);
   if (rc != VODB_OK) return rc;
 
   // every rank calls this the same number of times: the epoch (and its parity = buffer half) stay in lockstep
@@ -795,7 +855,7 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
     xd.peer_flag[r] = reinterpret_cast<uint32_t*>(base + x->off_flags()) + parity * kMaxPeers + x->rank;
   }
   if (s->n_added > 0) {
-    rc = run_scan(s, w.q_stage, nq, k, mode, safe != 0, nullptr, nullptr, st, &xd);
+    rc = run_scan(s, q_dev, q_dtype, nq, k, mode, safe != 0, nullptr, nullptr, st, &xd);
   } else {
     // an empty shard (more ranks than row blocks) contributes an all-padding list
     VODB_CUDA_CHECK(cudaMemsetAsync(w.cnt, 0, (size_t)nq * sizeof(int), st));

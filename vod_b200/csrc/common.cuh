@@ -70,6 +70,30 @@ __host__ __device__ __forceinline__ float ord_to_float(uint32_t o) {
 
 #define VODB_NEG_FLT_MAX (-3.402823466e+38f)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------
+// Every kernel of the search chain is launched with programmaticStreamSerializationAllowed: its CTAs may be
+// scheduled while the previous kernel of the stream is still draining, so launch latency and per-CTA set-up
+// (barrier init, TMEM allocation, descriptor prefetch) overlap the predecessor's tail. A kernel calls
+// pdl_launch_dependents() as early as possible and pdl_wait() before it touches anything a predecessor wrote.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- corpus store ---------------------------------------------------------------
 constexpr int kPitchAlign = 64;  // elements; one 128-byte TMA swizzle atom of 2-byte types
 
@@ -174,6 +198,10 @@ int launch_convert_rows(const void* src, int src_dtype, int src_dim, void* dst, 
 // queries -> `terms` planes of the 16-bit dtype: plane t holds round(q - sum of the previous planes)
 int launch_split_rows(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
                       int64_t plane_rows, int terms, cudaStream_t stream);
+// first kernel of a search: stage the queries (fp32 plane for EXACT, `terms` 16-bit planes for TENSOR) and reset the
+// candidate lists (cnt = rows of the first segment, tau = -inf) in one launch
+int launch_prepare(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
+                   int64_t plane_rows, int terms, int* cnt, float* tau, int first_rows, cudaStream_t stream);
 int launch_fill_synthetic(void* dst, int dtype, int dim, int pitch, uint64_t seed, int64_t global_row0, int64_t n,
                           int unit_norm, cudaStream_t stream);
 int launch_read_rows(const void* src, int dtype, int dim, int pitch, int64_t n, float* out, cudaStream_t stream);

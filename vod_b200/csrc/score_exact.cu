@@ -66,6 +66,8 @@ score_exact_kernel(const T* __restrict__ corpus, int pitch, int64_t row_begin, i
   const int64_t r0 = row_begin + (int64_t)blockIdx.x * BM;
   const int q0 = blockIdx.y * BN;
 
+  pdl_launch_dependents();
+  pdl_wait();  // staged queries, tau and the lists come from the preceding kernels of the stream
   if (tid < BN) tau_s[tid] = (q0 + tid < nq) ? tau[q0 + tid] : INFINITY;
 
   float acc[8][TN];
@@ -188,21 +190,22 @@ int launch_typed(const SegmentArgs& a, cudaStream_t stream) {
   int64_t tiles = (rows + BM - 1) / BM;
   const T* corpus = reinterpret_cast<const T*>(a.corpus);
   const float* q = reinterpret_cast<const float*>(a.queries);
+  cudaError_t e;
   // grid.x is limited to 2^31-1: fine for any shard that fits in HBM
   if (a.nq > 64) {
     dim3 grid((unsigned)tiles, (a.nq + 127) / 128);
-    score_exact_kernel<T, 128><<<grid, kThreads, 0, stream>>>(corpus, a.pitch, a.row_begin, a.row_end, q, a.nq,
+    e = launch_pdl(score_exact_kernel<T, 128>, grid, dim3(kThreads), 0, stream, corpus, a.pitch, a.row_begin, a.row_end, q, a.nq,
                                                               a.cand_s, a.cand_i, a.cnt, a.tau, a.overflow, a.cap, a.dump ? 1 : 0);
   } else if (a.nq > 32) {
     dim3 grid((unsigned)tiles, 1);
-    score_exact_kernel<T, 64><<<grid, kThreads, 0, stream>>>(corpus, a.pitch, a.row_begin, a.row_end, q, a.nq,
+    e = launch_pdl(score_exact_kernel<T, 64>, grid, dim3(kThreads), 0, stream, corpus, a.pitch, a.row_begin, a.row_end, q, a.nq,
                                                              a.cand_s, a.cand_i, a.cnt, a.tau, a.overflow, a.cap, a.dump ? 1 : 0);
   } else {
     dim3 grid((unsigned)tiles, 1);
-    score_exact_kernel<T, 32><<<grid, kThreads, 0, stream>>>(corpus, a.pitch, a.row_begin, a.row_end, q, a.nq,
+    e = launch_pdl(score_exact_kernel<T, 32>, grid, dim3(kThreads), 0, stream, corpus, a.pitch, a.row_begin, a.row_end, q, a.nq,
                                                              a.cand_s, a.cand_i, a.cnt, a.tau, a.overflow, a.cap, a.dump ? 1 : 0);
   }
-  VODB_CUDA_CHECK(cudaGetLastError());
+  VODB_CUDA_CHECK(e);
   return VODB_OK;
 }
 

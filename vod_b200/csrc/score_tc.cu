@@ -284,6 +284,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation) overlapped the previous kernel's tail; from here on the kernel
+  // reads what its predecessors wrote (staged queries, tau, cnt) and appends to the lists
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int n_items = p.n_ctiles * p.n_qtiles;
 
@@ -540,9 +544,8 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
   if (items <= 0) return VODB_OK;
   int grid = (int)(items < s->sm_count ? items : s->sm_count);
-  score_tc_kernel<BN, T><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(*reinterpret_cast<CUtensorMap*>(s->tmap_corpus),
-                                                                   tmap_q, p);
-  VODB_CUDA_CHECK(cudaGetLastError());
+  VODB_CUDA_CHECK(launch_pdl(score_tc_kernel<BN, T>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream,
+                             *reinterpret_cast<CUtensorMap*>(s->tmap_corpus), tmap_q, p));
   return VODB_OK;
 }
 

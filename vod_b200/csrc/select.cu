@@ -247,6 +247,8 @@ select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __r
   uint32_t* sel_o = reinterpret_cast<uint32_t*>(dyn + (size_t)P * sizeof(int32_t));
   uint32_t* cache = cache_n > 0 ? sel_o + P : nullptr;
   const int q = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();  // the scoring kernel's appends must be complete and visible
   const int n = min(cnt[q], cap);
   float* ls = cand_s + (size_t)q * cap;
   int32_t* li = cand_i + (size_t)q * cap;
@@ -334,6 +336,8 @@ merge_exchange_kernel(const float* __restrict__ gather_s, const int64_t* __restr
   __shared__ SelectSmem<int64_t> sm;
   int64_t* sel_i = reinterpret_cast<int64_t*>(dyn);
   uint32_t* sel_o = reinterpret_cast<uint32_t*>(dyn + (size_t)P * sizeof(int64_t));
+  pdl_launch_dependents();
+  pdl_wait();  // this rank's final select (which also filled slot `rank` of the local gather buffer) is complete
   if ((int)threadIdx.x < world) {
     uint32_t v;
     unsigned long long spins = 0;
@@ -400,10 +404,9 @@ int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap,
   }
   ExchangeDst none{};
   const int threads = (nq <= 512) ? 1024 : kSelThreads;  // few queries: more threads per list; many: more CTAs per SM
-  select_kernel<int32_t><<<nq, threads, smem, stream>>>(cand_s, cand_i, cnt, tau, cap, k, P, final_pass ? 1 : 0, out_s,
-                                                        out_i, row_offset, xd ? *xd : none,
-                                                        (xd && final_pass) ? 1 : 0, cache_n);
-  VODB_CUDA_CHECK(cudaGetLastError());
+  VODB_CUDA_CHECK(launch_pdl(select_kernel<int32_t>, dim3(nq), dim3(threads), smem, stream, cand_s, cand_i, cnt, tau, cap,
+                             k, P, final_pass ? 1 : 0, out_s, out_i, row_offset, xd ? *xd : none,
+                             (xd && final_pass) ? 1 : 0, cache_n));
   return VODB_OK;
 }
 
@@ -412,9 +415,8 @@ int launch_merge_exchange(const float* gather_s, const int64_t* gather_i, const 
                           cudaStream_t stream) {
   int P = pow2ceil(k);
   size_t smem = (size_t)P * (sizeof(int64_t) + sizeof(uint32_t));
-  merge_exchange_kernel<<<nq, kSelThreads, smem, stream>>>(gather_s, gather_i, flags, epoch, world, slot_elems, nq, k, P,
-                                                           out_s, out_i);
-  VODB_CUDA_CHECK(cudaGetLastError());
+  VODB_CUDA_CHECK(launch_pdl(merge_exchange_kernel, dim3(nq), dim3(kSelThreads), smem, stream, gather_s, gather_i, flags,
+                             epoch, world, slot_elems, nq, k, P, out_s, out_i));
   return VODB_OK;
 }
 
