@@ -260,9 +260,9 @@ def main():
     value = Q_SMALL / (ms_step * 1e-3)
     score_ms_per_search = max_over_ranks(prof["score_ms"] / args.steps)
     achieved_gbs = shard_bytes / (score_ms_per_search * 1e-3) / 1e9
-    # kernels per search on this rank: convert queries + init lists + (score, select) per segment (+ merge)
+    # kernels per search on this rank: prepare (query staging + list reset) + (score, select) per segment
     # (with N>1 the merge kernel is one more launch; the p2p exchange itself adds none, NCCL adds two collectives)
-    launches_per_step = 1 + int(stats["launches"]) + (1 if world > 1 else 0)
+    launches_per_step = int(stats["launches"]) + (1 if world > 1 else 0)
     roofline = {
         "bound": "hbm", "kernel": "score_tc_kernel<64> (tcgen05 + TMA, fused top-k filter)",
         "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
