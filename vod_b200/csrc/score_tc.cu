@@ -20,6 +20,9 @@
 // Algorithmic work per segment: rows*pitch*2 bytes from HBM, 2*nq*rows*pitch flop.
 #include <cuda.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vodb {
@@ -224,6 +227,90 @@ __device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
   return (j & 16) ? d[1] : d[0];
 }
 
+// ---- epilogue building blocks shared by the 1-CTA and the 2-CTA kernel ---------------------------------------
+
+// start of an item: fire the slot-reserving atomics for the previous item's survivors, load this query tile's
+// thresholds into the warp's own shared-memory copy (queries past nq never pass), recycle the flushed buffer
+template <int BN>
+__device__ __forceinline__ void epilogue_begin_item(const TcParams& p, WarpStage& ws, float* tau_cur, int q0, int sb,
+                                                    int local, int lane, PendingFlush& pend) {
+  if (!p.dump) {
+    if (local > 0) flush_issue(p, ws, sb ^ 1, lane, pend);
+    if (q0 + BN <= p.nq) {
+      for (int c = lane * 4; c < BN; c += 128)
+        *reinterpret_cast<float4*>(tau_cur + c) = *reinterpret_cast<const float4*>(p.tau + q0 + c);
+    } else {
+      for (int c = lane; c < BN; c += 32) tau_cur[c] = (q0 + c < p.nq) ? p.tau[q0 + c] : INFINITY;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) ws.count[sb ^ 1] = 0;  // every lane has read it; next pushed to two items from now
+}
+
+// the BN score columns of this thread's corpus row: dump them (first segment) or filter against tau and push the
+// rare survivors into the warp's staging buffer
+template <int BN>
+__device__ __forceinline__ void epilogue_columns(const TcParams& p, WarpStage& ws, const float* tau_cur,
+                                                 uint32_t taddr0, int64_t row, bool valid, int q0, int sb) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr0 + (uint32_t)c0, v);
+    tmem_ld_wait();
+    if (p.dump) {
+      // first segment: every score is a candidate; slot = row - row_begin, no atomics, coalesced over lanes
+      if (valid) {
+        const size_t slot = (size_t)(row - p.row_begin);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int q = q0 + c0 + j;
+          if (q < p.nq) {
+            p.cand_s[(size_t)q * p.cap + slot] = __uint_as_float(v[j]);
+            p.cand_i[(size_t)q * p.cap + slot] = (int32_t)row;
+          }
+        }
+      }
+      continue;
+    }
+    bool any = false;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 t = *reinterpret_cast<const float4*>(tau_cur + c0 + j4 * 4);
+      any |= (__uint_as_float(v[j4 * 4 + 0]) >= t.x) | (__uint_as_float(v[j4 * 4 + 1]) >= t.y) |
+             (__uint_as_float(v[j4 * 4 + 2]) >= t.z) | (__uint_as_float(v[j4 * 4 + 3]) >= t.w);
+    }
+    if (any && valid) {
+      // rare, divergent: this lane (= corpus row) has survivors among the 32 query columns. Build the column
+      // bitmask from registers, reserve staging slots with ONE shared-memory atomic, then push each set bit.
+      uint32_t m = 0;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 t = *reinterpret_cast<const float4*>(tau_cur + c0 + j4 * 4);
+        m |= (__uint_as_float(v[j4 * 4 + 0]) >= t.x ? 1u : 0u) << (j4 * 4 + 0);
+        m |= (__uint_as_float(v[j4 * 4 + 1]) >= t.y ? 1u : 0u) << (j4 * 4 + 1);
+        m |= (__uint_as_float(v[j4 * 4 + 2]) >= t.z ? 1u : 0u) << (j4 * 4 + 2);
+        m |= (__uint_as_float(v[j4 * 4 + 3]) >= t.w ? 1u : 0u) << (j4 * 4 + 3);
+      }
+      int idx = atomicAdd(&ws.count[sb], __popc(m));
+#pragma unroll 1
+      while (m != 0u) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1u;
+        const float sc = __uint_as_float(pick32(v, j));
+        const int q = q0 + c0 + j;
+        if (idx < kWarpStageCap) {
+          ws.s[sb][idx] = sc;
+          ws.row[sb][idx] = (int32_t)row;
+          ws.q[sb][idx] = q;
+        } else {
+          append_global(p.cnt, p.cand_s, p.cand_i, p.overflow, p.cap, q, sc, (int32_t)row);  // staging full: slow, correct
+        }
+        ++idx;
+      }
+    }
+  }
+}
+
 // BN = queries per tile (MMA N); T = query terms: a float32 query is split into T 16-bit terms (hi, lo, lo2) whose
 // partial products accumulate into the same TMEM accumulator, so T=2 keeps ~16 and T=3 all 24 mantissa bits of
 // the query while the corpus tile is loaded from HBM/L2 only once per stage.
@@ -362,19 +449,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       const uint32_t acc_phase = (local >> 1) & 1;
       const int q0 = qt * BN;
       const int sb = local & 1;  // staging buffer that receives this item's survivors
-      if (!p.dump) {
-        // append the previous item's survivors (atomics fired now, slots consumed after this item's columns)
-        if (local > 0) flush_issue(p, ws, sb ^ 1, lane, pend);
-        // this query tile's thresholds (queries past nq never pass)
-        if (q0 + BN <= p.nq) {
-          for (int c = lane * 4; c < BN; c += 128)
-            *reinterpret_cast<float4*>(tau_cur + c) = *reinterpret_cast<const float4*>(p.tau + q0 + c);
-        } else {
-          for (int c = lane; c < BN; c += 32) tau_cur[c] = (q0 + c < p.nq) ? p.tau[q0 + c] : INFINITY;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) ws.count[sb ^ 1] = 0;  // every lane has read it; next pushed to two items from now
+      epilogue_begin_item<BN>(p, ws, tau_cur, q0, sb, local, lane, pend);
 
       const int64_t row = p.row_begin + (int64_t)ct * BM + quarter * 32 + lane;
       const bool valid = row < p.row_end;
@@ -382,63 +457,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr0 + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (p.dump) {
-          // first segment: every score is a candidate; slot = row - row_begin, no atomics, coalesced over lanes
-          if (valid) {
-            const size_t slot = (size_t)(row - p.row_begin);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int q = q0 + c0 + j;
-              if (q < p.nq) {
-                p.cand_s[(size_t)q * p.cap + slot] = __uint_as_float(v[j]);
-                p.cand_i[(size_t)q * p.cap + slot] = (int32_t)row;
-              }
-            }
-          }
-          continue;
-        }
-        bool any = false;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 t = *reinterpret_cast<const float4*>(tau_cur + c0 + j4 * 4);
-          any |= (__uint_as_float(v[j4 * 4 + 0]) >= t.x) | (__uint_as_float(v[j4 * 4 + 1]) >= t.y) |
-                 (__uint_as_float(v[j4 * 4 + 2]) >= t.z) | (__uint_as_float(v[j4 * 4 + 3]) >= t.w);
-        }
-        if (any && valid) {
-          // rare, divergent: this lane (= corpus row) has survivors among the 32 query columns. Build the column
-          // bitmask from registers, reserve staging slots with ONE shared-memory atomic, then push each set bit.
-          uint32_t m = 0;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 t = *reinterpret_cast<const float4*>(tau_cur + c0 + j4 * 4);
-            m |= (__uint_as_float(v[j4 * 4 + 0]) >= t.x ? 1u : 0u) << (j4 * 4 + 0);
-            m |= (__uint_as_float(v[j4 * 4 + 1]) >= t.y ? 1u : 0u) << (j4 * 4 + 1);
-            m |= (__uint_as_float(v[j4 * 4 + 2]) >= t.z ? 1u : 0u) << (j4 * 4 + 2);
-            m |= (__uint_as_float(v[j4 * 4 + 3]) >= t.w ? 1u : 0u) << (j4 * 4 + 3);
-          }
-          int idx = atomicAdd(&ws.count[sb], __popc(m));
-#pragma unroll 1
-          while (m != 0u) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1u;
-            const float sc = __uint_as_float(pick32(v, j));
-            const int q = q0 + c0 + j;
-            if (idx < kWarpStageCap) {
-              ws.s[sb][idx] = sc;
-              ws.row[sb][idx] = (int32_t)row;
-              ws.q[sb][idx] = q;
-            } else {
-              append_global(p.cnt, p.cand_s, p.cand_i, p.overflow, p.cap, q, sc, (int32_t)row);  // staging full: slow, correct
-            }
-            ++idx;
-          }
-        }
-      }
+      epilogue_columns<BN>(p, ws, tau_cur, taddr0, row, valid, q0, sb);
       // all TMEM reads of this buffer are complete (wait::ld above): hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
@@ -457,6 +476,225 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- 2-CTA variant (cta_group::2) for large batches ------------------------------------------------------------
+//
+// A CTA pair (cluster of 2, one TPC) computes a [256 corpus rows x 256 queries] item with ONE tcgen05.mma issued by
+// the leader: each CTA stages only its own 128 corpus rows (A half) and its own 128 queries (B half) per K chunk
+// — 32 KB per stage instead of 48 KB for the same MMA work, i.e. 1/3 less L2->SM traffic and shared-memory write
+// bandwidth per flop than the 1-CTA 128x256 tile. Both CTAs keep their own 128 x 256 fp32 accumulator (two buffers,
+// all 512 TMEM columns) and run the same epilogue as the 1-CTA kernel on it.
+//   leader (cluster rank 0): TMA producer for its halves, MMA issuer for the pair, epilogue for rows 0..127
+//   follower (rank 1):       TMA producer for its halves (completes on the LEADER's full barrier), epilogue 128..255
+//   barriers: full[s] (leader) <- tx bytes of both CTAs; empty[s], tfull[a] (both CTAs) <- tcgen05.commit multicast;
+//             tempty[a] (leader) <- the 8 epilogue warps of the pair (follower warps arrive remotely).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address (-> leader CTA)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const void* tmap, uint64_t* leader_bar, void* smem_dst, int c0, int c1,
+                                                uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1),
+        "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in both CTAs of the pair once the MMAs issued so far finish
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+
+struct Tc2Config {
+  static constexpr int BN = 256;                       // queries per pair item (MMA N)
+  static constexpr uint32_t kABytes = BM * KC * 2;     // this CTA's 128 corpus rows
+  static constexpr uint32_t kBBytes = (BN / 2) * KC * 2;  // this CTA's 128 queries
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = 6;
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256 + 4 * BN * sizeof(float) + 4 * sizeof(WarpStage);
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_constant__ CUtensorMap tmap_query,
+                 const TcParams p) {
+  using Cfg = Tc2Config;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + STAGES * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* tau_s = reinterpret_cast<float*>(bars + 2 * STAGES + 6);
+  WarpStage* wst = reinterpret_cast<WarpStage*>(tau_s + 4 * BN);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader's expect_tx arrival; the bytes of both CTAs complete on it
+      mbar_init(&empty_bar[s], 1);  // one multicast commit per use
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
+    }
+    for (int w = 0; w < 4; ++w) wst[w].count[0] = wst[w].count[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();  // the peer's barriers exist before anything can signal them
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const int n_pairs = gridDim.x >> 1;
+  const int pair = blockIdx.x >> 1;
+  const int n_items = p.n_ctiles * p.n_qtiles;  // n_ctiles counts 256-row pair tiles here
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs) ----------------
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_corpus) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_query) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = pair; item < n_items; item += n_pairs) {
+        const int ct = item / p.n_qtiles, qt = item - ct * p.n_qtiles;
+        const int row0 = (int)(p.row_begin + ((int64_t)ct * 2 + rank) * BM);
+        const int q0 = qt * BN + (int)rank * (BN / 2);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          tma_load_2d_2sm(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC, row0, kEvictLast);
+          tma_load_2d_2sm(&tmap_query, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kc * KC, q0, kEvictLast);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ---------------- MMA issuer (leader only, for the pair) ----------------
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int item = pair; item < n_items; item += n_pairs, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = make_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < KC / UMMA_K; ++k)
+            umma_f16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kc | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);  // frees the stage in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull_bar[acc]);  // accumulators of both CTAs are complete
+      }
+    }
+  } else {
+    // ---------------- epilogue warps (2..5) of both CTAs ----------------
+    const int quarter = warp & 3;
+    const int ew = warp - 2;
+    WarpStage& ws = wst[ew];
+    float* tau_cur = tau_s + ew * BN;
+    int local = 0;
+    PendingFlush pend;
+#pragma unroll
+    for (int u = 0; u < kFlushPerLane; ++u) pend.pos[u] = -1;
+    for (int item = pair; item < n_items; item += n_pairs, ++local) {
+      const int ct = item / p.n_qtiles, qt = item - ct * p.n_qtiles;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int q0 = qt * BN;
+      const int sb = local & 1;
+      epilogue_begin_item<BN>(p, ws, tau_cur, q0, sb, local, lane, pend);
+
+      const int64_t row = p.row_begin + ((int64_t)ct * 2 + rank) * BM + quarter * 32 + lane;
+      const bool valid = row < p.row_end;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      epilogue_columns<BN>(p, ws, tau_cur, taddr0, row, valid, q0, sb);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&tempty_bar[acc], 0);  // the leader's barrier collects both CTAs' epilogues
+      flush_complete(p, pend);
+    }
+    __syncwarp();
+    if (!p.dump && local > 0) {
+      flush_issue(p, ws, (local - 1) & 1, lane, pend);
+      flush_complete(p, pend);
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();  // neither CTA may free TMEM / exit while the peer can still signal its barriers
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols)
                  : "memory");
   }
 }
@@ -549,6 +787,67 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   return VODB_OK;
 }
 
+int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
+  using Cfg = Tc2Config;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VODB_CUDA_CHECK(cudaFuncSetAttribute(score_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  if (!s->tmap_corpus_valid) {
+    int rc0 = encode_2d(reinterpret_cast<CUtensorMap*>(s->tmap_corpus), s->data, s->dtype, s->n_rows, s->pitch, BM);
+    if (rc0 != VODB_OK) return rc0;
+    s->tmap_corpus_valid = true;
+  }
+  alignas(64) CUtensorMap tmap_q;
+  const int64_t q_rows_pad = ((int64_t)a.nq + 255) / 256 * 256;
+  int rc = encode_2d(&tmap_q, a.queries, s->dtype, q_rows_pad, s->pitch, Cfg::BN / 2);
+  if (rc != VODB_OK) return rc;
+  TcParams p;
+  p.row_begin = a.row_begin;
+  p.row_end = a.row_end;
+  p.nq = a.nq;
+  p.n_ctiles = (int)((a.row_end - a.row_begin + 2 * BM - 1) / (2 * BM));  // 256-row pair tiles
+  p.n_qtiles = (a.nq + Cfg::BN - 1) / Cfg::BN;
+  p.kchunks = s->pitch / KC;
+  p.q_rows_pad = (int)q_rows_pad;
+  p.cand_s = a.cand_s;
+  p.cand_i = a.cand_i;
+  p.cnt = a.cnt;
+  p.tau = a.tau;
+  p.overflow = a.overflow;
+  p.cap = a.cap;
+  p.dump = a.dump ? 1 : 0;
+  const uint32_t fmt = (s->dtype == VODB_BF16) ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cfg::BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+  int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
+  if (items <= 0) return VODB_OK;
+  int pairs = (int)std::min<int64_t>(items, s->sm_count / 2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  VODB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, score_tc2_kernel, *reinterpret_cast<CUtensorMap*>(s->tmap_corpus), tmap_q, p));
+  return VODB_OK;
+}
+
+// the 2-CTA kernel serves large single-term batches; VODB_TC2=0 forces the 1-CTA kernel (A/B comparisons)
+bool use_pair_kernel(const SegmentArgs& a) {
+  static const char* env = std::getenv("VODB_TC2");
+  const bool enabled = env ? (env[0] != '0') : true;
+  return enabled && a.terms == 1 && a.nq > 128;
+}
+
 }  // namespace
 
 bool tensor_path_supported(const vodb_store* s) {
@@ -564,6 +863,7 @@ int launch_score_tensor(vodb_store* s, const SegmentArgs& a, cudaStream_t stream
     set_error("launch_score_tensor: shard too large for 32-bit TMA coordinates");
     return VODB_EUNSUPPORTED;
   }
+  if (use_pair_kernel(a)) return launch_pair(s, a, stream);
   switch (a.terms) {
     case 1:
       if (a.nq <= 64) return launch_bn<64, 1>(s, a, stream);
