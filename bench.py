@@ -354,8 +354,13 @@ def main():
             large = {
                 "queries_per_batch": Q_LARGE, "value": Q_LARGE / (ms_l * 1e-3), "unit": "queries/s", "ms_per_step": ms_l,
                 "steps": args.large_steps,
-                "roofline": {"bound": "tensor", "kernel": "score_tc_kernel<256>", "achieved": ach, "peak": peaks["bf16_tflops"],
+                "roofline": {"bound": "tensor",
+                             "kernel": "score_tc_kernel<256,1> (1-CTA)" if os.environ.get("VODB_TC2", "1")[0] == "0"
+                             else "score_tc2_kernel (cta_group::2 pair, 256 rows x 256 queries per MMA)",
+                             "achieved": ach, "peak": peaks["bf16_tflops"],
                              "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+                             "peak_sustained": peaks["bf16_tflops_sustained"],
+                             "frac_of_sustained": (ach / peaks["bf16_tflops_sustained"]) if peaks["bf16_tflops_sustained"] else None,
                              "score_kernel_ms_per_search": score_ms_l, "select_kernel_ms_per_search": prof_l["select_ms"] / args.large_steps,
                              "whole_step_frac": flops / (ms_l * 1e-3) / 1e12 / peaks["bf16_tflops"]},
                 "segments": int(stats_l["segments"]), "cap": int(stats_l["cap"]),
