@@ -74,3 +74,36 @@ def test_sharded_search_two_gpus():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] for r in results), results
+
+
+@pytest.mark.timeout(300)
+def test_single_process_multi_gpu_master():
+    """`B200SearchMaster(vectors, devices=[0, 1, ...])`: all GPUs of the box behind ONE drop-in master / client, the
+    analogue of faiss' index_cpu_to_all_gpus(shard=True) in the reference's single server process. Includes the
+    adversarial-order corpus, which forces the overflow-proof fallback on every shard."""
+    import torch
+
+    import vod_b200
+    from oracle import flat_ip
+    from tests.helpers import int_valued
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    devices = list(range(min(torch.cuda.device_count(), 4)))
+    rng = np.random.default_rng(3)
+    vectors, xq = int_valued(rng, (30_011, 96)), int_valued(rng, (33, 96))
+    rs, ri = flat_ip.search(vectors, xq, 50)
+    with vod_b200.B200SearchMaster(vectors, dtype="bfloat16", devices=devices) as master:
+        assert master.store.ntotal == len(vectors)
+        out = master.get_client().search(vector=xq, top_k=50)
+        assert np.array_equal(out.indices, ri) and np.array_equal(out.scores, rs)
+    n = 400_000
+    adv = np.zeros((n, 64), np.float32)
+    adv[:, 0] = (np.arange(n) // 64) % 256
+    adv[:, 1] = np.arange(n) // (64 * 256)
+    q = np.zeros((3, 64), np.float32)
+    q[:, 0], q[:, 1] = 1.0, 256.0
+    rs, ri = flat_ip.search(adv, q, 100)
+    with vod_b200.B200SearchMaster(adv, dtype="bfloat16", devices=devices[:2], mode="tensor") as master:
+        out = master.get_client().search(vector=q, top_k=100)
+        assert np.array_equal(out.indices, ri) and np.array_equal(out.scores, rs)

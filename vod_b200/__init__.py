@@ -14,11 +14,11 @@ from .search import (B200SearchClient, B200SearchMaster, CorpusStore, DoNotPickl
                      build_b200_index, merge_topk, merge_topk_device)
 from .hybrid import async_hybrid_search, merge_search_results, normalize_search_scores_
 from .routing import ShardedSearchClient
-from .sharded import ShardedCorpus, ShardedSearcher, shard_bounds
+from .sharded import MultiGpuStore, ShardedCorpus, ShardedSearcher, shard_bounds
 
 __all__ = [
     "B200SearchClient", "B200SearchMaster", "CorpusStore", "DenseRetrievalSampler", "sample_device", "DoNotPickleError", "PrioritySampledSections",
-    "RetrievalBatch", "RetrievalSample", "RetrievalTuple", "SearchClient", "ShardedCorpus", "ShardedSearchClient",
+    "RetrievalBatch", "RetrievalSample", "RetrievalTuple", "SearchClient", "MultiGpuStore", "ShardedCorpus", "ShardedSearchClient",
     "ShardedSearcher", "async_hybrid_search", "merge_search_results", "normalize_search_scores_",
     "VodbError", "VodbUnavailableError", "build_b200_index", "labeled_priority_sampling", "merge_topk",
     "merge_topk_device", "priority_sampling_1d", "sample_search_results", "shard_bounds",

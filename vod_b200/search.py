@@ -394,7 +394,8 @@ class B200SearchMaster:
 
     def __init__(self, vectors: typ.Any = None, *, dtype: str = "float32", device: int = 0, mode: str | None = None,
                  row_offset: int = 0, add_batch_size: int = 1 << 18, skip_setup: bool = False,
-                 free_resources: bool = False, store: CorpusStore | None = None, serve: bool = True):
+                 free_resources: bool = False, store: CorpusStore | None = None, serve: bool = True,
+                 devices: typ.Sequence[int] | None = None):
         self.vectors = vectors
         self.dtype = dtype
         self.device = device
@@ -406,6 +407,7 @@ class B200SearchMaster:
         self.store: CorpusStore | None = store
         self._owns_store = store is None
         self.master_id = next(_master_ids)
+        self.devices = list(devices) if devices else [device]  # >1: row-shard over several GPUs in this process
         self.serve = serve  # expose the store to other processes (DataLoader workers) over a Unix socket
         self._server = None
 
@@ -437,7 +439,7 @@ class B200SearchMaster:
         if self.vectors is None:
             raise ValueError("B200SearchMaster needs `vectors` (or an existing `store`)")
         self.store = build_b200_index(self.vectors, dtype=self.dtype, device=self.device, row_offset=self.row_offset,
-                                      add_batch_size=self.add_batch_size)
+                                      add_batch_size=self.add_batch_size, devices=self.devices)
 
     def get_client(self) -> B200SearchClient:
         srv = self._server
@@ -472,7 +474,8 @@ def _slice_rows(vectors: typ.Any, start: int, stop: int) -> np.ndarray:
 
 
 def build_b200_index(vectors: typ.Any, *, dtype: str = "float32", device: int = 0, row_offset: int = 0,
-                     add_batch_size: int = 1 << 18, factory_string: str = "Flat") -> CorpusStore:
+                     add_batch_size: int = 1 << 18, factory_string: str = "Flat",
+                     devices: typ.Sequence[int] | None = None) -> typ.Any:
     """Build the HBM store from a sequence of 1-D vectors — the analogue of `build_faiss_index`
     (build.py:12-81) for `factory_string="Flat"` with the inner-product metric.
 
@@ -488,7 +491,12 @@ def build_b200_index(vectors: typ.Any, *, dtype: str = "float32", device: int = 
     if len(vector_shape) > 1:
         raise ValueError(f"Only 1D vectors can be handled. Found shape `{vector_shape}`")
     dim = int(vector_shape[-1])
-    store = CorpusStore(n, dim, dtype=dtype, device=device, row_offset=row_offset)
+    if devices is not None and len(devices) > 1:  # `index_cpu_to_all_gpus(index, co.shard=True)` analogue, one process
+        from .sharded import MultiGpuStore
+
+        store = MultiGpuStore(n, dim, dtype=dtype, devices=devices)
+    else:
+        store = CorpusStore(n, dim, dtype=dtype, device=devices[0] if devices else device, row_offset=row_offset)
     for i in range(0, n, add_batch_size):
         batch = _slice_rows(vectors, i, min(n, i + add_batch_size))
         store.add(batch, row0=i)

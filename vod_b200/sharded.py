@@ -183,3 +183,89 @@ class ShardedCorpus:
             _lib.load().vodb_xchg_destroy(self._xchg)
             self._xchg = None
         self.store.close()
+
+
+class MultiGpuStore:
+    """All GPUs of the box driven from ONE process: the drop-in analogue of the reference's
+    `faiss.index_cpu_to_all_gpus(index, co)` with `co.shard = True` inside its single server process
+    (src/vod_search/faiss_search/server.py:51-54). One `CorpusStore` per device holds the contiguous row block
+    `shard_bounds(n, G, g)`; a search enqueues the G local scans back to back (they run concurrently, one stream
+    per device), copies the G small [B,k] results to the first device over NVLink and merges them there
+    (`vodb_merge_topk`). Same `search(vectors, top_k)` / `ntotal` / `close()` surface as `CorpusStore`.
+    """
+
+    def __init__(self, n_rows: int, dim: int, dtype: str = "bfloat16", devices: typ.Sequence[int] = (0,)):
+        from .search import CorpusStore
+
+        self.devices = list(devices)
+        self.n_rows, self.dim = int(n_rows), int(dim)
+        self.bounds = [shard_bounds(self.n_rows, len(self.devices), g) for g in range(len(self.devices))]
+        self.stores = [CorpusStore(hi - lo, dim, dtype=dtype, device=d, row_offset=lo)
+                       for d, (lo, hi) in zip(self.devices, self.bounds)]
+        self.device = self.devices[0]
+
+    @property
+    def ntotal(self) -> int:
+        return sum(st.ntotal for st in self.stores)
+
+    @property
+    def dtype(self) -> str:
+        return self.stores[0].dtype
+
+    def add(self, rows: typ.Any, row0: int | None = None) -> None:
+        """Write global rows [row0, row0+len(rows)) into the shards they belong to."""
+        row0 = self.ntotal if row0 is None else int(row0)
+        n = len(rows)
+        for st, (lo, hi) in zip(self.stores, self.bounds):
+            a, b = max(row0, lo), min(row0 + n, hi)
+            if a < b:
+                st.add(rows[a - row0:b - row0], row0=a - lo)
+
+    def fill_synthetic(self, seed: int, unit_norm: bool = False) -> None:
+        for st, (lo, hi) in zip(self.stores, self.bounds):
+            st.fill_synthetic(seed, 0, hi - lo, unit_norm=unit_norm)
+
+    def search(self, vectors: np.ndarray, top_k: int, mode: str | int | None = None) -> tuple[np.ndarray, np.ndarray]:
+        import torch
+
+        from .search import merge_topk_device
+
+        q = np.ascontiguousarray(vectors)
+        if q.ndim != 2:
+            raise ValueError(f"Expected 2D array, got {q.ndim}D array")
+        if q.shape[1] != self.dim:
+            raise ValueError(f"query dimension {q.shape[1]} != index dimension {self.dim}")
+        if q.dtype not in (np.float32, np.float16):
+            q = q.astype(np.float32)
+        for safe_pass in (False, True):
+            parts = []
+            q_host = torch.from_numpy(q)
+            for st in self.stores:  # enqueue everything first: the G scans overlap
+                if st.ntotal == 0:
+                    continue
+                with torch.cuda.device(st.device):
+                    qd = q_host.to(f"cuda:{st.device}", non_blocking=True)
+                    if safe_pass:
+                        s_np, i_np = st.search(q, top_k, mode=mode)  # synchronous entry point: overflow-proof fallback inside
+                        parts.append((torch.from_numpy(s_np).to(f"cuda:{self.device}"), torch.from_numpy(i_np).to(f"cuda:{self.device}")))
+                    else:
+                        parts.append(st.search_device(qd, top_k, mode=mode))
+            dev0 = torch.device(f"cuda:{self.device}")
+            with torch.cuda.device(dev0):
+                for st in self.stores:  # device 0 must see the other devices' results
+                    if st.device != self.device:
+                        torch.cuda.current_stream(dev0).wait_stream(torch.cuda.current_stream(st.device))
+                all_s = torch.stack([s.to(dev0, non_blocking=True) for s, _ in parts])
+                all_i = torch.stack([i.to(dev0, non_blocking=True) for _, i in parts])
+                ms, mi = merge_topk_device(all_s, all_i, top_k)
+                out = ms.cpu().numpy(), mi.cpu().numpy()
+            if safe_pass or not any(st.check_async() for st in self.stores if st.ntotal):
+                return out
+        raise AssertionError("unreachable")
+
+    def stats(self) -> dict[str, int]:
+        return self.stores[0].stats()
+
+    def close(self) -> None:
+        for st in self.stores:
+            st.close()
