@@ -322,3 +322,30 @@ def test_pickled_client_reaches_the_gpu_master_from_a_worker_process():
         ok, s, i = q.get(timeout=150)
         p.join(timeout=30)
     assert ok and np.array_equal(s, local.scores) and np.array_equal(i, local.indices)
+
+
+def test_pair_kernel_overflow_fallback_and_odd_tile_counts():
+    """The 2-CTA kernel (batches > 128 queries): adversarial row order -> list overflow -> overflow-proof schedule;
+    segment / shard sizes that leave the follower CTA of the last pair without rows."""
+    n, d = 150_000 + 128, 64   # odd number of 128-row tiles
+    xb = np.zeros((n, d), np.float32)
+    xb[:, 0] = (np.arange(n) // 64) % 256
+    xb[:, 1] = np.arange(n) // (64 * 256)
+    xq = np.zeros((130, d), np.float32)
+    xq[:, 0] = 1.0
+    xq[:, 1] = 256.0
+    xq[:, 2] = np.arange(130)  # distinct queries, same ranking
+    st = _store(xb, "bfloat16")
+    s, i = st.search(xq, 100, mode="tensor")
+    rs, ri = flat_ip.search(xb, xq, 100)
+    assert np.array_equal(i, ri) and np.array_equal(s, rs)
+    assert st.stats()["safe_fallback"] == 1
+    st.close()
+    rng = np.random.default_rng(31)
+    for rows in (129, 257, 128 * 7 + 5):
+        xb2, xq2 = int_valued(rng, (rows, 128)), int_valued(rng, (200, 128))
+        st = _store(xb2, "float16")
+        s, i = st.search(xq2, 100, mode="tensor")
+        rs, ri = flat_ip.search(xb2, xq2, 100)
+        assert np.array_equal(i, ri) and np.array_equal(s, rs)
+        st.close()
