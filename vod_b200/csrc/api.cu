@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -30,6 +31,23 @@ void set_error(const char* fmt, ...) {
   g_error = buf;
 }
 const char* get_error() { return g_error.c_str(); }
+
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = done[{kernel, dev}];
+  if (bytes > cur) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    cur = bytes;
+  }
+  return cudaSuccess;
+}
 
 struct ProfileState {
   std::vector<cudaEvent_t> pool;

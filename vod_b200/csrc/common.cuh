@@ -94,6 +94,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: remember what has been set for
+// (kernel, current device) so that stores on several GPUs of one process all get it (api.cu)
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes);
+
 // ---- corpus store ---------------------------------------------------------------
 constexpr int kPitchAlign = 64;  // elements; one 128-byte TMA swizzle atom of 2-byte types
 

@@ -248,11 +248,7 @@ int launch_typed(const MergeArgs& a, int M, void* out_scores, int64_t* out_indic
     set_error("vodb_merge_results: %d entries per row need %zu bytes of shared memory (limit 220 KB)", M, smem);
     return VODB_EUNSUPPORTED;
   }
-  static size_t max_set = 48 * 1024;
-  if (smem > max_set) {
-    VODB_CUDA_CHECK(cudaFuncSetAttribute(merge_results_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    max_set = 220 * 1024;
-  }
+  if (smem > 48 * 1024) VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&merge_results_kernel<F>), 220 * 1024));
   merge_results_kernel<F><<<a.B, kThreads, smem, st>>>(a, M, P, reinterpret_cast<F*>(out_scores), out_indices,
                                                        out_labels, reinterpret_cast<F*>(out_raw), out_counts);
   VODB_CUDA_CHECK(cudaGetLastError());

@@ -282,15 +282,11 @@ int launch_sample(const float* scores, const uint8_t* labels, const float* noise
   if (B == 0) return VODB_OK;
   int P = pow2ceil_i(K > 1 ? K : 2);
   size_t smem = (size_t)P * 8 + (size_t)K * 8 + (size_t)((K + 15) / 16) * 16 + (size_t)k_total * 4 + 16;
-  static size_t max_set = 48 * 1024;
-  if (smem > max_set) {
-    if (smem > 220 * 1024) {
-      set_error("vodb_sample: K=%d needs %zu bytes of shared memory (limit 220 KB)", K, smem);
-      return VODB_EUNSUPPORTED;
-    }
-    VODB_CUDA_CHECK(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    max_set = smem;
+  if (smem > 220 * 1024) {
+    set_error("vodb_sample: K=%d needs %zu bytes of shared memory (limit 220 KB)", K, smem);
+    return VODB_EUNSUPPORTED;
   }
+  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&sample_kernel), smem));
   sample_kernel<<<B, NT, smem, stream>>>(scores, labels, noise, K, P, k_positive, k_total, normalized, temperature,
                                          max_support, quirks, seed, offset, out_ids, out_logw, out_labels, out_lse);
   VODB_CUDA_CHECK(cudaGetLastError());

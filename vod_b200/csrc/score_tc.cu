@@ -745,12 +745,7 @@ template <int BN, int T>
 int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   using Cfg = TcConfig<BN, T>;
   static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
-  static bool attr_set = false;
-  if (!attr_set) {
-    VODB_CUDA_CHECK(cudaFuncSetAttribute(score_tc_kernel<BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&score_tc_kernel<BN, T>), Cfg::kSmemBytes));
   if (!s->tmap_corpus_valid) {
     int rc = encode_2d(reinterpret_cast<CUtensorMap*>(s->tmap_corpus), s->data, s->dtype, s->n_rows, s->pitch, BM);
     if (rc != VODB_OK) return rc;
@@ -789,11 +784,7 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
 
 int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   using Cfg = Tc2Config;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VODB_CUDA_CHECK(cudaFuncSetAttribute(score_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&score_tc2_kernel), Cfg::kSmemBytes));
   if (!s->tmap_corpus_valid) {
     int rc0 = encode_2d(reinterpret_cast<CUtensorMap*>(s->tmap_corpus), s->data, s->dtype, s->n_rows, s->pitch, BM);
     if (rc0 != VODB_OK) return rc0;

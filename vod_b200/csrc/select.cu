@@ -397,11 +397,7 @@ int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap,
   int cache_n = std::min(std::max(expected_n, 0), std::min(cap, 32768));
   cache_n = (cache_n + 255) / 256 * 256;
   size_t smem = (size_t)P * (sizeof(int32_t) + sizeof(uint32_t)) + (size_t)cache_n * sizeof(uint32_t);
-  static size_t max_set = 48 * 1024;
-  if (smem > max_set) {
-    VODB_CUDA_CHECK(cudaFuncSetAttribute(select_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024)));
-    max_set = 160 * 1024;
-  }
+  if (smem > 48 * 1024) VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&select_kernel<int32_t>), 160 * 1024));
   ExchangeDst none{};
   const int threads = (nq <= 512) ? 1024 : kSelThreads;  // few queries: more threads per list; many: more CTAs per SM
   VODB_CUDA_CHECK(launch_pdl(select_kernel<int32_t>, dim3(nq), dim3(threads), smem, stream, cand_s, cand_i, cnt, tau, cap,
