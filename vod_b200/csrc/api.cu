@@ -397,11 +397,11 @@ int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes) {
   }
   size_t out_need = (size_t)nq * k;
   if (out_need > w.out_cap) {
-    if (w.out_s) cudaFree(w.out_s);
-    if (w.out_i) cudaFree(w.out_i);
-    w.out_s = nullptr; w.out_i = nullptr;
-    VODB_CUDA_CHECK(cudaMalloc(&w.out_s, out_need * sizeof(float)));
-    VODB_CUDA_CHECK(cudaMalloc(&w.out_i, out_need * sizeof(int64_t)));
+    if (w.out_pack) cudaFree(w.out_pack);
+    if (w.out_host) cudaFreeHost(w.out_host);
+    w.out_pack = nullptr; w.out_host = nullptr;
+    VODB_CUDA_CHECK(cudaMalloc(&w.out_pack, out_need * 12 + 16));
+    VODB_CUDA_CHECK(cudaMallocHost(&w.out_host, out_need * 12 + 16));
     w.out_cap = out_need;
   }
   return VODB_OK;
@@ -410,7 +410,8 @@ int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes) {
 void free_workspace(Workspace& w) {
   cudaFree(w.cand_s); cudaFree(w.cand_i); cudaFree(w.cnt); cudaFree(w.tau); cudaFree(w.overflow);
   if (w.overflow_host) cudaFreeHost(w.overflow_host);
-  cudaFree(w.q_stage); cudaFree(w.q_in); cudaFree(w.out_s); cudaFree(w.out_i);
+  cudaFree(w.q_stage); cudaFree(w.q_in); cudaFree(w.out_pack);
+  if (w.out_host) cudaFreeHost(w.out_host);
   w = Workspace();
 }
 
@@ -741,24 +742,26 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
   rc = upload_queries(s, queries, q_dtype, q_on_device, nq, st, &q_dev);
   if (rc != VODB_OK) return rc;
 
-  float* o_s = out_on_device ? out_scores : w.out_s;
-  int64_t* o_i = out_on_device ? out_idx : w.out_i;
+  const size_t nqk = (size_t)nq * k;
+  int64_t* pack_i = reinterpret_cast<int64_t*>(w.out_pack);
+  float* pack_s = reinterpret_cast<float*>(w.out_pack + nqk * 8);
   if (out_on_device) {
     // asynchronous: only enqueue. A list overflow leaves the sticky device flag set; the caller polls it
     // with vodb_search_check() (bench / pipelined callers) and re-runs synchronously if it fired.
-    return run_scan(s, q_dev, q_dtype, nq, k, mode, /*safe=*/false, o_s, o_i, st);
+    return run_scan(s, q_dev, q_dtype, nq, k, mode, /*safe=*/false, out_scores, out_idx, st);
   }
-  // host outputs: results and the overflow flag come back with ONE synchronisation; if a list overflowed (rare)
-  // the batch is re-run on the overflow-proof schedule and copied again
+  // host outputs: ids, scores and the overflow flag come back with ONE device->host copy (pinned mirror) and ONE
+  // synchronisation; if a list overflowed (rare) the batch is re-run on the overflow-proof schedule
   bool safe = false;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    rc = run_scan(s, q_dev, q_dtype, nq, k, mode, safe, o_s, o_i, st);
+    rc = run_scan(s, q_dev, q_dtype, nq, k, mode, safe, pack_s, pack_i, st);
     if (rc != VODB_OK) return rc;
-    VODB_CUDA_CHECK(cudaMemcpyAsync(w.overflow_host, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
-    VODB_CUDA_CHECK(cudaMemcpyAsync(out_scores, w.out_s, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-    VODB_CUDA_CHECK(cudaMemcpyAsync(out_idx, w.out_i, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VODB_CUDA_CHECK(cudaMemcpyAsync(w.out_pack + nqk * 12, w.overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    VODB_CUDA_CHECK(cudaMemcpyAsync(w.out_host, w.out_pack, nqk * 12 + sizeof(int), cudaMemcpyDeviceToHost, st));
     VODB_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (*w.overflow_host == 0) break;
+    int flag;
+    std::memcpy(&flag, w.out_host + nqk * 12, sizeof(int));
+    if (flag == 0) break;
     VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
     if (safe) {
       set_error("vodb_search: candidate list overflow in safe mode (internal error)");
@@ -766,6 +769,8 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
     }
     safe = true;  // re-run with segments that cannot overflow
   }
+  std::memcpy(out_idx, w.out_host, nqk * 8);
+  std::memcpy(out_scores, w.out_host + nqk * 8, nqk * 4);
   return VODB_OK;
 }
 
@@ -880,17 +885,19 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
     rc = launch_select(w.cand_s, w.cand_i, w.cnt, w.tau, w.cap, nq, k, true, nullptr, nullptr, s->row_offset, st, &xd);
   }
   if (rc != VODB_OK) return rc;
-  float* o_s = out_on_device ? out_scores : w.out_s;
-  int64_t* o_i = out_on_device ? out_idx : w.out_i;
+  const size_t nqk = (size_t)nq * k;
+  float* o_s = out_on_device ? out_scores : reinterpret_cast<float*>(w.out_pack + nqk * 8);
+  int64_t* o_i = out_on_device ? out_idx : reinterpret_cast<int64_t*>(w.out_pack);
   const float* gs = reinterpret_cast<const float*>(x->local + x->off_s()) + (size_t)parity * x->world * x->slot;
   const int64_t* gi = reinterpret_cast<const int64_t*>(x->local + x->off_i()) + (size_t)parity * x->world * x->slot;
   const uint32_t* flags = reinterpret_cast<const uint32_t*>(x->local + x->off_flags()) + parity * kMaxPeers;
   rc = launch_merge_exchange(gs, gi, flags, x->epoch, x->world, x->slot, nq, k, o_s, o_i, st);
   if (rc != VODB_OK) return rc;
   if (!out_on_device) {
-    VODB_CUDA_CHECK(cudaMemcpyAsync(out_scores, w.out_s, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-    VODB_CUDA_CHECK(cudaMemcpyAsync(out_idx, w.out_i, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VODB_CUDA_CHECK(cudaMemcpyAsync(w.out_host, w.out_pack, nqk * 12, cudaMemcpyDeviceToHost, st));
     VODB_CUDA_CHECK(cudaStreamSynchronize(st));
+    std::memcpy(out_idx, w.out_host, nqk * 8);
+    std::memcpy(out_scores, w.out_host + nqk * 8, nqk * 4);
   }
   return VODB_OK;
 }

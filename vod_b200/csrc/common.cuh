@@ -117,9 +117,11 @@ struct Workspace {
   size_t q_stage_bytes = 0;
   void* q_in = nullptr;  // raw copy of host queries
   size_t q_in_bytes = 0;
-  float* out_s = nullptr;
-  int64_t* out_i = nullptr;
-  size_t out_cap = 0;  // elements
+  // staged outputs of host callers: one device buffer [ids i64 x nqk | scores f32 x nqk | overflow flag] so that
+  // results and flag come back with ONE device->host copy into the pinned mirror
+  char* out_pack = nullptr;
+  char* out_host = nullptr;  // pinned
+  size_t out_cap = 0;        // elements (nq * k) the pack can hold
 };
 
 }  // namespace vodb
