@@ -26,9 +26,9 @@ if [[ $STEP == all || $STEP == bench ]]; then
   run bench_ref 600 python bench.py --impl reference --steps 5 --warmup 2
 fi
 if [[ $STEP == all || $STEP == ncu ]]; then
-  run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --large-steps 1
-  run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:score_tc -s 4 -c 4 -o gpurun_out/prof_score_tc python bench.py --steps 2 --warmup 1 --no-cpu --no-large
-  run ncu_full256 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'score_tc_kernel<.int.256,' -s 4 -c 4 -o gpurun_out/prof_score_tc256 python bench.py --steps 1 --warmup 1 --no-cpu --large-steps 1
+  run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --large-steps 1
+  run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:score_tc_kernel -s 4 -c 4 -o gpurun_out/prof_score_tc python bench.py --steps 2 --warmup 1 --no-cpu --no-large
+  run ncu_full256 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:score_tc2_kernel -s 7 -c 7 -o gpurun_out/prof_score_tc256 python bench.py --steps 1 --warmup 1 --no-cpu --large-steps 1
 fi
 if [[ $STEP == all || $STEP == sanitizer ]]; then
   run sanitizer_memcheck 600 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitizer_probe.py
