@@ -1,0 +1,90 @@
+"""Builds profiles/r01_summary.md from the committed captures (bench lines, ncu launch list, ncu raw pages)."""
+import csv, json, pathlib
+P = pathlib.Path(__file__).resolve().parents[1] / "profiles"
+def bench(name): return json.loads((P / name).read_text().strip().splitlines()[-1])
+out = []; A = out.append
+A("# Round 1 — profile summary (B200, sm_100a)\n")
+A("All numbers from `gpurun` boxes (1x B200 unless noted). Peaks: `MEASURED_PEAKS.json` — HBM 6534.8 GB/s (copy kernel), bf16 1671.7 TFLOP/s burst / 1404.1 sustained (cuBLAS). Workload: BASELINE configs[1], 10M x 768 bf16, exact top-100. Box-to-box variation of the same build is about +-4% (2.19-2.29 ms for the 64-query step).\n")
+A("Files: `r01a_*` first working tcgen05 path; `r01b_*` dump mode + staged survivors; `r01c..g_*` bench lines along the way; `r01h_*` final state of the round (launch list, `ncu --set full` raw pages of `score_tc_kernel<64,1>` and the 2-CTA `score_tc2_kernel`, bench lines of both arms); `r01i_*` final multi-GPU bench lines; probes: `r01_schedule_sweep.jsonl`, `r01_query_terms_probe.json`, `r01_configs_3_5_probe.json`, `r01_compute_sanitizer.txt`. Regenerate this file with `python scripts/make_profile_summary.py`.\n")
+d = bench("r01h_bench.json"); f = bench("r01f_bench.json")
+A("## Headline (r01h_bench.json; r01f_bench.json is the same build on another box)\n")
+A("| quantity | r01h | r01f |\n|---|---|---|")
+A(f"| 64-query batches, inputs resident in HBM: queries/s (ms/step) | {d['value']:.0f} ({d['ms_per_step']:.4f}) | {f['value']:.0f} ({f['ms_per_step']:.4f}) |")
+A(f"| corpus scanned, whole step | {d['corpus_gb_per_s']:.0f} GB/s = {d['roofline']['whole_step_frac']*100:.1f}% of measured HBM peak | {f['corpus_gb_per_s']:.0f} GB/s = {f['roofline']['whole_step_frac']*100:.1f}% |")
+A(f"| scoring kernel alone (CUDA events around its launches) | {d['roofline']['score_kernel_ms_per_search']:.4f} ms = {d['roofline']['achieved']:.0f} GB/s = {d['roofline']['frac']*100:.1f}% | {f['roofline']['score_kernel_ms_per_search']:.4f} ms = {f['roofline']['achieved']:.0f} GB/s = {f['roofline']['frac']*100:.1f}% |")
+A(f"| select kernels per search | {d['roofline']['select_kernel_ms_per_search']*1e3:.1f} us | {f['roofline']['select_kernel_ms_per_search']*1e3:.1f} us |")
+A(f"| e2e through `B200SearchClient.search(np.ndarray)` (pinned H2D 196 KB + D2H 77 KB inside): queries/s (ms) | {d['e2e']['value']:.0f} ({d['e2e']['ms_per_step']:.3f}) | {f['e2e']['value']:.0f} ({f['e2e']['ms_per_step']:.3f}) |")
+A(f"| per-call latency p10 / p50 / p90 (ms) | {d['latency']['p10']:.3f} / {d['latency']['p50']:.3f} / {d['latency']['p90']:.3f} | {f['latency']['p10']:.3f} / {f['latency']['p50']:.3f} / {f['latency']['p90']:.3f} |")
+c4 = d['config4_retrieve_and_sample']
+A(f"| config 4 chain (32 queries -> top-1000 -> sample 8, host in, [32,8] out) | p50 {c4['chain_ms_p50']:.3f} ms; sampler kernel p50 {c4['sampler_kernel_us_p50']:.1f} us | - |")
+lb, lf = d['large_batch'], f['large_batch']
+A(f"| 8192-query batches: queries/s (ms/step) | {lb['value']:.0f} ({lb['ms_per_step']:.1f}) 2-CTA kernel | {lf['value']:.0f} ({lf['ms_per_step']:.1f}) 1-CTA kernel |")
+A(f"| 8192-query scoring kernels | {lb['roofline']['achieved']:.0f} TFLOP/s = {lb['roofline']['frac']*100:.1f}% of burst peak, {lb['roofline']['frac_of_sustained']*100:.1f}% of sustained | {lf['roofline']['achieved']:.0f} TFLOP/s = {lf['roofline']['frac']*100:.1f}% |")
+A(f"| CPU baseline (oracle port: numpy/OpenBLAS sgemm + exact top-k, {d['cpu_baseline']['cores']} host cores, 500k-row sample x20) | {d['cpu_baseline']['value']:.1f} queries/s | - |")
+A(f"| kernels per 64-query search | {d['gpu_launches_per_step']} (prepare + 4 x (score, select)), all launched with PDL | |")
+A(f"| clocks during the timed region | {d['clocks']} | |\n")
+A("## Strong scaling, same 10M-row corpus (queries/s, 64-query batches)\n")
+A("| GPUs | exchange | file | queries/s | ms/step | vs 1 GPU of the same series | 8192-query batch q/s |\n|---|---|---|---|---|---|---|")
+series = [("early (before select/PDL work)", [(1, 'r01c_bench.json'), (2, 'r01c_bench_n2_p2p.json'), (2, 'r01c_bench_n2_nccl.json'), (4, 'r01d_bench_n4_p2p.json'), (8, 'r01d_bench_n8_p2p.json'), (8, 'r01d_bench_n8_nccl.json')]),
+          ("final", [(1, 'r01h_bench.json'), (2, 'r01i_bench_n2_p2p.json'), (4, 'r01i_bench_n4_p2p.json'), (8, 'r01i_bench_n8_p2p.json'), (8, 'r01i_bench_n8_nccl.json')])]
+for label, files in series:
+    base = None
+    for n, fn in files:
+        if not (P / fn).exists(): continue
+        x = bench(fn)
+        if n == 1: base = x['value']
+        ex = '-' if n == 1 else ('p2p (fused into select / merge kernels)' if 'p2p' in fn else 'NCCL all-gather')
+        l = (x.get('large_batch') or {}).get('value')
+        A(f"| {n} ({label}) | {ex} | {fn} | {x['value']:.0f} | {x['ms_per_step']:.4f} | {x['value']/base:.2f}x | {'%.0f' % l if l else '-'} |")
+A("")
+lines = [l for l in open(P / 'r01h_launches_ncu.csv') if not l.startswith('==')]
+r = list(csv.DictReader(lines))
+# first complete search = first 'prepare' after the synthetic fill
+start = next(i for i, row in enumerate(r) if 'prepare_kernel' in row['Kernel Name'])
+start = next(i for i, row in enumerate(r) if 'prepare_kernel' in row['Kernel Name'] and i > start)
+A("## One 64-query search, per launch (ncu launch list r01h_launches_ncu.csv: cold cache, serialised)\n")
+A("| # | kernel | grid x block | us |\n|---|---|---|---|")
+tot = sc = 0
+for row in r[start:start + 9]:
+    name = row['Kernel Name']; short = name.split('>::')[-1].split('(')[0]
+    us = float(row['Metric Value']) / 1e3; tot += us
+    if 'score_tc' in short: sc += us
+    A(f"| {row['ID']} | `{short}` | {row['Grid Size']} x {row['Block Size']} | {us:.1f} |")
+A(f"\nScoring kernel share of the search under ncu: {sc/tot*100:.1f}% ({sc:.0f} of {tot:.0f} us); from bench.py's CUDA events without profiler: {d['roofline']['score_kernel_ms_per_search']/d['ms_per_step']*100:.1f}%. The shares agree.\n")
+def table(path, title, algo_rows, elt=1536):
+    rows = list(csv.reader(open(P / path))); hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
+    A(f"## {title}\n")
+    A("| segment | rows | ms | DRAM read GB (algorithmic GB) | DRAM write MB | DRAM % of peak | tensor pipe active % | L2 throughput % | L2 hit % | SM clock GHz |\n|---|---|---|---|---|---|---|---|---|---|")
+    for j, rr in enumerate(rows[2:]):
+        g = lambda k: rr[idx[k]]
+        nrows = algo_rows[j] if j < len(algo_rows) else 0
+        A(f"| {j} | {nrows} | {float(g('gpu__time_duration.sum')):.4f} | {float(g('dram__bytes_read.sum')):.3f} ({nrows*elt/1e9:.3f}) | {float(g('dram__bytes_write.sum')):.1f} | {float(g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | {float(g('TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed')):.1f} | {float(g('lts__throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | {float(g('lts__t_sector_hit_rate.pct')):.1f} | {float(g('sm__cycles_elapsed.avg.per_second')):.3f} |")
+    A("")
+table('r01h_score_tc64_ncu_raw.csv', "ncu --set full, `score_tc_kernel<64,1>` (64 queries), the 4 segments of one search", [4096, 83840, 1800960, 8111104])
+A("DRAM traffic equals the algorithmic bytes (15.36 GB read per search, +0.07%): nothing is re-read, the score matrix never exists. The two large segments run at 6.9-7.0 TB/s (84-85% of ncu's DRAM peak, 106% of the copy-kernel figure) with the tensor pipe 16-20% busy: HBM-bound as designed. 128 registers, 1 CTA/SM, 192 threads.\n")
+table('r01h_score_tc2_pair_ncu_raw.csv', "ncu --set full, `score_tc2_kernel` (2-CTA pairs, 8192 queries), the 7 segments of one search", [4096, 12288, 49152, 196608, 786432, 3145728, 5805696])
+A("The large segments keep the tensor pipe 83-87% active at 1.41-1.44 GHz (sw_power_cap): the kernel sits at the MMA issue limit at the clock the 1 kW budget allows. Against the 1-CTA capture (`r01e_score_tc256_ncu_raw.csv`: 86-90% active at 1.38 GHz, L2 throughput 67-72%) the pair kernel moves 1/3 less data per flop (L2 throughput 50%), which buys the higher clock. Early segments (dense survivors, few items per pair) are below that; they cover 10% of the rows.\n")
+A("## Epilogue history (8192-query batch, segment with ~19 survivors per 128x256 item)\n")
+A("| version | that segment | whole batch |\n|---|---|---|")
+A("| r01a: warp-aggregated global atomic per surviving column, L2 round trip inside the epilogue | 93 ms, 20% of the MMA rate | 190.5 ms, 39.7% of peak |")
+A("| r01b: dump mode for segment 0, CTA-level smem staging + bulk flush behind block barriers | 60 ms | 141.3 ms, 52.7% |")
+A("| + two-phase flush (issue atomics, consume after the item), register bitmask push | 50 ms | 134.2 ms, 58.3% |")
+A("| r01c: per-warp staging (no block barriers), select-tree push, growth 3 for large batches | not distinguishable | 98.5 ms, 77.7% |")
+A("| r01g/h: 2-CTA pair kernel, PDL | - | 95.3-98.4 ms, 78-80% of burst / 93-95% of sustained peak |\n")
+A("ncu source-level sampling that drove this (r01b capture, epilogue warps): 15% of samples on the unrolled per-column bit tests, 15% at the block barrier waiting for warps in the push path, 11% instruction-cache misses in the unrolled push code.\n")
+t = json.loads((P / 'r01_query_terms_probe.json').read_text().strip().splitlines()[-1])
+A("## Query-term modes (r01_query_terms_probe.json; 10M x 768 bf16, float32 queries NOT representable in bf16)\n")
+A("| mode | 64-query ms | 8192-query ms | recall@100 vs fp32 CUDA-core kernel |\n|---|---|---|---|")
+for m in ('tensor', 'tensor2', 'tensor3'):
+    A(f"| {m} | {t[m+'_q64_ms']:.3f} | {t[m+'_q8192_ms']:.1f} | {t[m+'_recall_vs_exact']:.4f} |")
+A(f"| exact (fp32 FMA, CUDA cores) | {t['exact_q64_ms']:.2f} | - | 1 |\n")
+c = json.loads((P / 'r01_configs_3_5_probe.json').read_text().strip().splitlines()[-1])
+A("## BASELINE configs 3 and 5, one GPU's share (r01_configs_3_5_probe.json, scripts/probe_configs.py)\n")
+A("| config | result |\n|---|---|")
+A(f"| C3 shard: 12.5M x 768 fp16 (= 100M rows over 8 GPUs), top-1000, 64 queries | {c['c3_q64_k1000_ms']:.3f} ms per batch = {c['c3_q64_GBps']:.0f} GB/s ({c['c3_q64_GBps']/65.348:.0f}% of measured HBM peak), {c['c3_q64_segments']} segments, list capacity {c['c3_q64_cap']} |")
+A(f"| C3 shard, 8192 queries, top-1000 | {c['c3_q8192_k1000_ms']:.1f} ms = {c['c3_q8192_TFLOPs']:.0f} TFLOP/s ({c['c3_q8192_TFLOPs']/16.717:.0f}% of measured bf16 peak; 1-CTA kernel at the time) |")
+A(f"| C5 shard: 6.25M x 1024 (= 50M rows over 8 GPUs), fp32 host vectors -> bf16 store, 2^18-row chunks from pinned memory | {c['c5_ingest_s']:.3f} s = {c['c5_ingest_host_GBps']:.1f} GB/s of host data (PCIe Gen5 x16 bound); from a CUDA fp32 tensor (encoder output): {c['c5_ingest_from_device_s']*1e3:.1f} ms |")
+A(f"| C5 search, fp32-exact, 64 queries, top-100 | tensor cores, 3 query terms: {c['c5_search_tensor3_ms']:.2f} ms; CUDA-core fp32 kernel: {c['c5_search_exact_ms']:.1f} ms (same neighbours: recall {c['c5_tensor3_vs_exact_recall']:.1f}, max relative score difference {c['c5_tensor3_vs_exact_max_rel_score_diff']:.0e}); 1 term: {c['c5_search_tensor_ms']:.2f} ms |\n")
+A("## compute-sanitizer\n\n`scripts/sanitizer_probe.py` (every kernel, small sizes): memcheck 0 errors, racecheck 0 hazards (`r01_compute_sanitizer.txt`).")
+(P / 'r01_summary.md').write_text("\n".join(out) + "\n")
+print("wrote", P / 'r01_summary.md')
