@@ -143,8 +143,8 @@ int vodb_merge_topk(int device, const float* scores, const int64_t* idx, int n_l
  *
  * Replaces faiss' IndexShards host-side merge (index_cpu_to_all_gpus with co.shard=True, server.py:51-54) and the
  * NCCL all-gather of the unfused path: the final select kernel of every rank stores its [nq,k] (score, global id)
- * list directly into every peer's gather buffer and publishes an epoch flag; the merge kernel waits on its own
- * flags and reduces world*k -> k. Set-up: every rank calls vodb_xchg_create, the 64-byte handles are all-gathered
+ * list directly into every peer's gather buffer as epoch-tagged 8-byte words (payload and tag in one atomic store,
+ * no fence, no flag); the merge kernel spins on the tags of the entries it reads and reduces world*k -> k. Set-up: every rank calls vodb_xchg_create, the 64-byte handles are all-gathered
  * by the host code (torch.distributed), then every rank calls vodb_xchg_connect with the world*64 handle bytes
  * (rank-major). All ranks must then call vodb_search_sharded the same number of times, in the same order. */
 #define VODB_IPC_HANDLE_BYTES 64

@@ -524,8 +524,8 @@ int run_scan(vodb_store* s, const void* q_dev, int q_dtype, int nq, int k, int m
 
 using namespace vodb;
 
-// Peer-mapped exchange buffers of one rank (vodb_xchg_*): [flags 2 x kMaxPeers u32 | pad to 256 B |
-// gather scores 2 x world x slot f32 | gather ids 2 x world x slot i64], exported to the peers through CUDA IPC.
+// Peer-mapped exchange buffer of one rank (vodb_xchg_*): [2 parities][world source ranks][slot entries][3 tagged
+// 8-byte words] (see ExchangeDst), zero-initialised, exported to the peers through CUDA IPC.
 struct vodb_xchg {
   int device = 0, rank = 0, world = 1;
   int max_nq = 0, max_k = 0;
@@ -534,11 +534,7 @@ struct vodb_xchg {
   char* local = nullptr;      // this rank's buffer
   char* peer[kMaxPeers] = {}; // peer-mapped base pointers (peer[rank] == local)
   bool connected = false;
-  int* done_counter = nullptr;
   uint32_t epoch = 0;
-  static size_t off_flags() { return 0; }
-  static size_t off_s() { return 256; }
-  size_t off_i() const { return off_s() + (((size_t)2 * world * slot * sizeof(float)) + 255) / 256 * 256; }
 };
 
 namespace {
@@ -789,18 +785,15 @@ int vodb_xchg_create(vodb_xchg** out, int device, int rank, int world, int max_n
   if (!x) return VODB_ENOMEM;
   x->device = device; x->rank = rank; x->world = world; x->max_nq = max_nq; x->max_k = max_k;
   x->slot = (size_t)max_nq * max_k;
-  x->bytes = x->off_i() + (size_t)2 * world * x->slot * sizeof(int64_t);
+  x->bytes = (size_t)2 * world * x->slot * 3 * sizeof(uint64_t);
   cudaError_t e = cudaMalloc(&x->local, x->bytes);
   if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&x->done_counter, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(x->done_counter, 0, sizeof(int));
   cudaIpcMemHandle_t h;
   if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, x->local);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     set_error("vodb_xchg_create: %s", cudaGetErrorString(e));
     if (x->local) cudaFree(x->local);
-    if (x->done_counter) cudaFree(x->done_counter);
     delete x;
     cudaGetLastError();
     return VODB_ECUDA;
@@ -839,7 +832,6 @@ void vodb_xchg_destroy(vodb_xchg* x) {
   for (int r = 0; r < x->world; ++r)
     if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
   if (x->local) cudaFree(x->local);
-  if (x->done_counter) cudaFree(x->done_counter);
   delete x;
 }
 
@@ -870,13 +862,8 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
   xd.world = x->world;
   xd.rank = x->rank;
   xd.epoch = x->epoch;
-  xd.done_counter = x->done_counter;
-  for (int r = 0; r < x->world; ++r) {
-    char* base = x->peer[r];
-    xd.peer_s[r] = reinterpret_cast<float*>(base + x->off_s()) + ((size_t)parity * x->world + x->rank) * x->slot;
-    xd.peer_i[r] = reinterpret_cast<int64_t*>(base + x->off_i()) + ((size_t)parity * x->world + x->rank) * x->slot;
-    xd.peer_flag[r] = reinterpret_cast<uint32_t*>(base + x->off_flags()) + parity * kMaxPeers + x->rank;
-  }
+  for (int r = 0; r < x->world; ++r)
+    xd.peer_ll[r] = reinterpret_cast<uint64_t*>(x->peer[r]) + ((size_t)parity * x->world + x->rank) * x->slot * 3;
   if (s->n_added > 0) {
     rc = run_scan(s, q_dev, q_dtype, nq, k, mode, safe != 0, nullptr, nullptr, st, &xd);
   } else {
@@ -888,10 +875,8 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
   const size_t nqk = (size_t)nq * k;
   float* o_s = out_on_device ? out_scores : reinterpret_cast<float*>(w.out_pack + nqk * 8);
   int64_t* o_i = out_on_device ? out_idx : reinterpret_cast<int64_t*>(w.out_pack);
-  const float* gs = reinterpret_cast<const float*>(x->local + x->off_s()) + (size_t)parity * x->world * x->slot;
-  const int64_t* gi = reinterpret_cast<const int64_t*>(x->local + x->off_i()) + (size_t)parity * x->world * x->slot;
-  const uint32_t* flags = reinterpret_cast<const uint32_t*>(x->local + x->off_flags()) + parity * kMaxPeers;
-  rc = launch_merge_exchange(gs, gi, flags, x->epoch, x->world, x->slot, nq, k, o_s, o_i, st);
+  const uint64_t* gll = reinterpret_cast<const uint64_t*>(x->local) + (size_t)parity * x->world * x->slot * 3;
+  rc = launch_merge_exchange(gll, x->epoch, x->world, x->slot, nq, k, o_s, o_i, st);
   if (rc != VODB_OK) return rc;
   if (!out_on_device) {
     VODB_CUDA_CHECK(cudaMemcpyAsync(w.out_host, w.out_pack, nqk * 12, cudaMemcpyDeviceToHost, st));

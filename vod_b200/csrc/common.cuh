@@ -169,18 +169,18 @@ struct SegmentArgs {
   bool dump;            // first segment of a scan: lists are empty, every score is stored at slot row-row_begin
 };
 
-// Cross-shard exchange fused into the final select (select.cu): every rank's final select kernel stores its [nq,k]
-// result straight into slot `rank` of every peer's gather buffer (peer-mapped memory, NVLink stores), the last CTA
-// publishes an epoch flag on every peer, and the merge kernel spins on its own flags before reducing world*k -> k.
+// Cross-shard exchange fused into the final select (select.cu), NCCL-LL style: every rank's final select kernel
+// stores its [nq,k] result straight into slot `rank` of every peer's gather buffer (peer-mapped memory, NVLink
+// stores) as three 8-byte words per entry, each carrying 4 payload bytes and the 4-byte epoch tag of the call:
+//   w0 = epoch<<32 | score bits, w1 = epoch<<32 | id[31:0], w2 = epoch<<32 | id[63:32].
+// An aligned 8-byte store is single-copy atomic, so a reader that sees the tag also sees the payload: no fences, no
+// flags, no counters. The merge kernel spins on the tags of the entries it needs and reduces world*k -> k.
 constexpr int kMaxPeers = 16;
 struct ExchangeDst {
   int world;
   int rank;
   uint32_t epoch;
-  int* done_counter;                 // local: CTAs of the final select that have finished their stores
-  float* peer_s[kMaxPeers];          // peer r's gather scores, slot `rank`, current parity
-  int64_t* peer_i[kMaxPeers];
-  uint32_t* peer_flag[kMaxPeers];    // peer r's flags[parity][rank]
+  uint64_t* peer_ll[kMaxPeers];  // peer r's gather buffer, slot `rank`, current parity: [nq*k][3] words
 };
 
 int launch_score_exact(const SegmentArgs& a, int sm_count, cudaStream_t stream);
@@ -191,10 +191,9 @@ bool tensor_path_supported(const vodb_store* s);
 int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap, int nq, int k, bool final,
                   float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream,
                   const ExchangeDst* xd = nullptr, int expected_n = 0);
-// merge of the gathered per-rank lists after waiting for every peer's epoch flag (see ExchangeDst)
-int launch_merge_exchange(const float* gather_s, const int64_t* gather_i, const uint32_t* flags, uint32_t epoch,
-                          int world, size_t slot_elems, int nq, int k, float* out_s, int64_t* out_i,
-                          cudaStream_t stream);
+// merge of the gathered per-rank lists; waits for every entry's epoch tag (see ExchangeDst)
+int launch_merge_exchange(const uint64_t* gather_ll, uint32_t epoch, int world, size_t slot_elems, int nq, int k,
+                          float* out_s, int64_t* out_i, cudaStream_t stream);
 int launch_merge(const float* scores, const int64_t* idx, int n_lists, int nq, int k_in, int k_out, float* out_s,
                  int64_t* out_i, cudaStream_t stream);
 int launch_init_lists(int* cnt, float* tau, int first_rows, int nq, cudaStream_t stream);

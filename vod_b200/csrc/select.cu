@@ -258,26 +258,20 @@ select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __r
   int n_sel = block_select<int32_t>(load_s, load_i, n, k, final_pass != 0, sm, sel_o, sel_i, P, cache, cache_n, &vstar);
   __syncthreads();
   if (final_pass && use_xd) {
-    // fused exchange: store this shard's result into every rank's gather buffer (own rank included)
+    // fused exchange: store this shard's result into every rank's gather buffer (own rank included) as
+    // tagged 8-byte words; nothing else is needed to publish it
+    const uint64_t tag = (uint64_t)xd.epoch << 32;
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
       const float sv = (j < n_sel) ? ord_to_float(sel_o[j]) : VODB_NEG_FLT_MAX;
       const int64_t iv = (j < n_sel) ? (int64_t)sel_i[j] + row_offset : (int64_t)-1;
+      const uint64_t w0 = tag | (uint64_t)__float_as_uint(sv);
+      const uint64_t w1 = tag | (uint64_t)(uint32_t)iv;
+      const uint64_t w2 = tag | (uint64_t)(uint32_t)((uint64_t)iv >> 32);
       for (int r = 0; r < xd.world; ++r) {
-        xd.peer_s[r][(size_t)q * k + j] = sv;
-        xd.peer_i[r][(size_t)q * k + j] = iv;
-      }
-    }
-    // one system-scope fence per CTA: the barrier orders every thread's peer stores before thread 0's fence, which
-    // (cumulativity) makes them visible system-wide before the counter / flag updates that follow
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence_system();
-      const int done = atomicAdd(xd.done_counter, 1);
-      if (done == (int)gridDim.x - 1) {  // last CTA: every CTA's stores are fenced; publish the epoch on every peer
-        *xd.done_counter = 0;
-        __threadfence_system();
-        for (int r = 0; r < xd.world; ++r)
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xd.peer_flag[r]), "r"(xd.epoch) : "memory");
+        uint64_t* dst = xd.peer_ll[r] + ((size_t)q * k + j) * 3;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(w0) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(w1) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 2), "l"(w2) : "memory");
       }
     }
   } else if (final_pass) {
@@ -327,38 +321,42 @@ merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, 
   }
 }
 
-// Merge after the fused exchange: wait until every source rank has published `epoch`, then reduce world*k -> k.
+// Merge after the fused exchange: every entry is read with a spin on its epoch tag (entries of this rank's own
+// select are already there; a peer's arrive as its final select runs), then world*k -> k as in merge_kernel.
+__device__ __forceinline__ uint64_t ll_wait_word(const uint64_t* p, uint32_t epoch) {
+  uint64_t v;
+  unsigned long long spins = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if ((uint32_t)(v >> 32) == epoch) return v;
+    if (++spins > (1ull << 31)) {  // a peer never arrived: fail loudly instead of hanging the GPU
+      printf("vodb: exchange timeout (epoch %u, word tag %u)\n", epoch, (uint32_t)(v >> 32));
+      __trap();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kSelThreads)
-merge_exchange_kernel(const float* __restrict__ gather_s, const int64_t* __restrict__ gather_i,
-                      const uint32_t* __restrict__ flags, uint32_t epoch, int world, size_t slot_elems, int nq, int k,
-                      int P, float* __restrict__ out_s, int64_t* __restrict__ out_i) {
+merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, int world, size_t slot_elems, int nq,
+                      int k, int P, float* __restrict__ out_s, int64_t* __restrict__ out_i) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ SelectSmem<int64_t> sm;
   int64_t* sel_i = reinterpret_cast<int64_t*>(dyn);
   uint32_t* sel_o = reinterpret_cast<uint32_t*>(dyn + (size_t)P * sizeof(int64_t));
   pdl_launch_dependents();
   pdl_wait();  // this rank's final select (which also filled slot `rank` of the local gather buffer) is complete
-  if ((int)threadIdx.x < world) {
-    uint32_t v;
-    unsigned long long spins = 0;
-    for (;;) {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
-      if ((int32_t)(v - epoch) >= 0) break;
-      if (++spins > (1ull << 31)) {  // a peer never arrived: fail loudly instead of hanging the GPU
-        printf("vodb: exchange timeout waiting for rank %d (epoch %u, flag %u)\n", (int)threadIdx.x, epoch, v);
-        __trap();
-      }
-    }
-  }
-  __syncthreads();
   const int q = blockIdx.x;
   const int n = world * k;
-  auto off_of = [&](int i) -> size_t {
+  auto entry = [&](int i) -> const uint64_t* {
     int l = i / k, j = i - l * k;
-    return (size_t)l * slot_elems + (size_t)q * k + j;
+    return gather_ll + ((size_t)l * slot_elems + (size_t)q * k + j) * 3;
   };
-  auto load_s = [&](int i) -> float { return gather_s[off_of(i)]; };
-  auto load_i = [&](int i) -> int64_t { return gather_i[off_of(i)]; };
+  auto load_s = [&](int i) -> float { return __uint_as_float((uint32_t)ll_wait_word(entry(i), epoch)); };
+  auto load_i = [&](int i) -> int64_t {
+    const uint64_t* e = entry(i);
+    uint64_t lo = ll_wait_word(e + 1, epoch), hi = ll_wait_word(e + 2, epoch);
+    return (int64_t)((lo & 0xffffffffull) | (hi << 32));
+  };
   uint32_t vstar;
   int n_sel = block_select<int64_t>(load_s, load_i, n, k, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar);
   __syncthreads();
@@ -406,13 +404,12 @@ int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap,
   return VODB_OK;
 }
 
-int launch_merge_exchange(const float* gather_s, const int64_t* gather_i, const uint32_t* flags, uint32_t epoch,
-                          int world, size_t slot_elems, int nq, int k, float* out_s, int64_t* out_i,
-                          cudaStream_t stream) {
+int launch_merge_exchange(const uint64_t* gather_ll, uint32_t epoch, int world, size_t slot_elems, int nq, int k,
+                          float* out_s, int64_t* out_i, cudaStream_t stream) {
   int P = pow2ceil(k);
   size_t smem = (size_t)P * (sizeof(int64_t) + sizeof(uint32_t));
-  VODB_CUDA_CHECK(launch_pdl(merge_exchange_kernel, dim3(nq), dim3(kSelThreads), smem, stream, gather_s, gather_i, flags,
-                             epoch, world, slot_elems, nq, k, P, out_s, out_i));
+  VODB_CUDA_CHECK(launch_pdl(merge_exchange_kernel, dim3(nq), dim3(kSelThreads), smem, stream, gather_ll, epoch, world,
+                             slot_elems, nq, k, P, out_s, out_i));
   return VODB_OK;
 }
 

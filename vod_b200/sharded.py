@@ -11,8 +11,9 @@ the contiguous row block `shard_bounds(n_total, world, rank)`; a search is
 
 Two exchange implementations, same results:
   * exchange="p2p" (default on GPUs): fused into the kernels. The final select kernel of every rank stores its list
-    straight into every peer's gather buffer (CUDA-IPC peer-mapped memory, NVLink stores) and publishes an epoch
-    flag; the merge kernel spins on its own flags. No collective library call, no extra launch
+    straight into every peer's gather buffer (CUDA-IPC peer-mapped memory, NVLink stores) as epoch-tagged 8-byte
+    words (NCCL-LL style: tag and payload in one atomic store, no fence); the merge kernel spins on the tags of the
+    entries it reads. No collective library call, no extra launch
     (`vodb_search_sharded`, include/vodb.h).
   * exchange="nccl": one `all_gather_into_tensor` per array over NCCL, then `vodb_merge_topk`.
 The exchanged payload is B*k*12 bytes per rank (77 KB at B=64, k=100).
