@@ -99,26 +99,9 @@ __global__ void convert_rows_kernel(const S* __restrict__ src, int src_dim, D* _
   }
 }
 
-// float32 query -> `terms` 16-bit planes: plane t = round(q - plane_0 - ... - plane_{t-1}). The partial sums are
-// exact in float32 (each remainder is a float32 with fewer significant bits), so 3 bf16 / 2-3 fp16 terms
-// reproduce the float32 value exactly (barring fp16 range limits).
-template <typename S, typename D>
-__global__ void split_rows_kernel(const S* __restrict__ src, int src_dim, D* __restrict__ dst, int dst_pitch, int64_t n,
-                                  int64_t plane_rows, int terms) {
-  int64_t total = n * dst_pitch;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = e / dst_pitch;
-    int c = (int)(e - r * dst_pitch);
-    float v = (c < src_dim) ? to_f32<S>(src[r * src_dim + c]) : 0.0f;
-    for (int t = 0; t < terms; ++t) {
-      D d = from_f32<D>(v);
-      dst[(size_t)t * plane_rows * dst_pitch + e] = d;
-      v = __fsub_rn(v, to_f32<D>(d));
-    }
-  }
-}
-
-// prepare = query staging + list reset. dst dtype float: one plane (EXACT mode); 16-bit: `terms` planes.
+// prepare = query staging + list reset. dst dtype float: one plane (EXACT mode); 16-bit: `terms` planes, plane t =
+// round(q - plane_0 - ... - plane_{t-1}). The remainders are exact in float32 (each has fewer significant bits), so
+// 3 bf16 / 2-3 fp16 terms reproduce the float32 query exactly (barring fp16 range limits).
 template <typename S, typename D>
 __global__ void prepare_kernel(const S* __restrict__ src, int src_dim, D* __restrict__ dst, int dst_pitch, int64_t n,
                                int64_t plane_rows, int terms, int* __restrict__ cnt, float* __restrict__ tau,
@@ -231,35 +214,6 @@ int launch_convert_rows(const void* src, int src_dtype, int src_dim, void* dst, 
     case VODB_F32: return convert_dispatch_dst<float>(src, src_dim, dst, dst_dtype, dst_pitch, n, st);
     case VODB_BF16: return convert_dispatch_dst<__nv_bfloat16>(src, src_dim, dst, dst_dtype, dst_pitch, n, st);
     case VODB_F16: return convert_dispatch_dst<__half>(src, src_dim, dst, dst_dtype, dst_pitch, n, st);
-  }
-  set_error("bad src dtype %d", src_dtype);
-  return VODB_EINVAL;
-}
-
-namespace {
-template <typename S>
-int split_dispatch_dst(const void* src, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
-                       int64_t plane_rows, int terms, cudaStream_t st) {
-  int64_t total = n * dst_pitch;
-  if (total == 0) return VODB_OK;
-  int g = grid_for(total);
-  const S* s = reinterpret_cast<const S*>(src);
-  switch (dst_dtype) {
-    case VODB_BF16: split_rows_kernel<S, __nv_bfloat16><<<g, 256, 0, st>>>(s, src_dim, (__nv_bfloat16*)dst, dst_pitch, n, plane_rows, terms); break;
-    case VODB_F16: split_rows_kernel<S, __half><<<g, 256, 0, st>>>(s, src_dim, (__half*)dst, dst_pitch, n, plane_rows, terms); break;
-    default: set_error("launch_split_rows: destination must be a 16-bit dtype, got %d", dst_dtype); return VODB_EINVAL;
-  }
-  VODB_CUDA_CHECK(cudaGetLastError());
-  return VODB_OK;
-}
-}  // namespace
-
-int launch_split_rows(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
-                      int64_t plane_rows, int terms, cudaStream_t st) {
-  switch (src_dtype) {
-    case VODB_F32: return split_dispatch_dst<float>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, st);
-    case VODB_BF16: return split_dispatch_dst<__nv_bfloat16>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, st);
-    case VODB_F16: return split_dispatch_dst<__half>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, st);
   }
   set_error("bad src dtype %d", src_dtype);
   return VODB_EINVAL;

@@ -196,13 +196,9 @@ int launch_merge_exchange(const uint64_t* gather_ll, uint32_t epoch, int world, 
                           float* out_s, int64_t* out_i, cudaStream_t stream);
 int launch_merge(const float* scores, const int64_t* idx, int n_lists, int nq, int k_in, int k_out, float* out_s,
                  int64_t* out_i, cudaStream_t stream);
-int launch_init_lists(int* cnt, float* tau, int first_rows, int nq, cudaStream_t stream);
 
 int launch_convert_rows(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch,
                         int64_t n, cudaStream_t stream);
-// queries -> `terms` planes of the 16-bit dtype: plane t holds round(q - sum of the previous planes)
-int launch_split_rows(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
-                      int64_t plane_rows, int terms, cudaStream_t stream);
 // first kernel of a search: stage the queries (fp32 plane for EXACT, `terms` 16-bit planes for TENSOR) and reset the
 // candidate lists (cnt = rows of the first segment, tau = -inf) in one launch
 int launch_prepare(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,

@@ -367,24 +367,7 @@ merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, in
   }
 }
 
-// cnt starts at the row count of the first scan segment: that segment stores every score at slot row-row_begin
-// ("dump" mode of the scoring kernels), so the lists are pre-sized instead of grown with atomics.
-// The overflow flag is sticky: cleared by the host after it has been read (vodb_search / vodb_search_check).
-__global__ void init_lists_kernel(int* cnt, float* tau, int first_rows, int nq) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nq) {
-    cnt[i] = first_rows;
-    tau[i] = -INFINITY;
-  }
-}
-
 }  // namespace
-
-int launch_init_lists(int* cnt, float* tau, int first_rows, int nq, cudaStream_t stream) {
-  init_lists_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(cnt, tau, first_rows, nq);
-  VODB_CUDA_CHECK(cudaGetLastError());
-  return VODB_OK;
-}
 
 int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap, int nq, int k, bool final_pass,
                   float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream, const ExchangeDst* xd,
