@@ -15,6 +15,8 @@
  *                                      src/vod_search/faiss_search/server.py:51-54
  *   vodb_sample                     <- _labeled_priority_sampling_2d_ (numba)
  *                                      src/vod_dataloaders/core/sample.py:323-352 (and :245-320, :160-219)
+ *   vodb_retrieve_sample            <- RealmCollate: search -> sample_search_results, dense-only flow
+ *                                      src/vod_dataloaders/realm_collate.py:101-122, core/sample.py:22-84
  *   vodb_store_ntotal / _dim        <- index.ntotal / index.d checks, build.py:75-79; server.py:59-66
  *
  * Conventions
@@ -197,6 +199,27 @@ int vodb_sample(int device, const float* scores, const uint8_t* labels, const fl
                 int K, int k_positive, int k_total, int normalized, float temperature,
                 int max_support, int quirks, uint64_t seed, uint64_t offset, int64_t* out_ids,
                 float* out_logw, uint8_t* out_labels, float* out_lse, int on_device, void* stream);
+
+/* ---- retrieve -> sample chain --------------------------------------------- */
+
+/* What RealmCollate does per training batch with the dense engine alone (realm_collate.py:101-122), in one call and
+ * without the [nq, top_k] lists leaving HBM: vodb_search(top_k) -> labels[b,j] = (retrieved id in gold_ids[b,:]) ->
+ * vodb_sample(k_positive, k_total, normalized=1) -> sample_search_results' gathers (core/sample.py:57-71).
+ *   queries      as vodb_search (host or device pointer)
+ *   gold_ids     host int64 [nq, n_gold] ids of the positive sections (negative entries = padding), NULL if n_gold == 0
+ *   out_idx      host int64  [nq,k_total]  global row ids at the picks
+ *   out_scores   host float32[nq,k_total]  retrieval scores at the picks
+ *   out_logw / out_labels / out_lse        as vodb_sample
+ *   out_msid     host float32[nq]          max_sampling_id (sample.py:66-71)
+ *   out_local    host int64  [nq,k_total]  optional (NULL ok): positions inside the top_k list, -1 in unused slots
+ * Unused slots (sampler position -1) gather the LAST retrieved column, like numpy's take_along_axis in the reference.
+ * Results equal vodb_search + host labels + vodb_sample + numpy gathers bit for bit. Synchronous; one device->host
+ * copy of the packed [nq, k_total] result. top_k <= VODB_MAX_K. */
+int vodb_retrieve_sample(vodb_store* store, const void* queries, int q_dtype, int q_on_device, int nq, int top_k,
+                         int mode, const int64_t* gold_ids, int n_gold, int k_positive, int k_total,
+                         float temperature, int max_support, int quirks, uint64_t seed, uint64_t offset,
+                         int64_t* out_idx, float* out_scores, float* out_logw, uint8_t* out_labels, float* out_lse,
+                         float* out_msid, int64_t* out_local, void* stream);
 
 #ifdef __cplusplus
 }

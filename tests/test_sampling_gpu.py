@@ -203,5 +203,43 @@ def test_device_resident_retrieve_then_sample_equals_host_path():
     assert np.array_equal(dev.batch.labels, host.batch.labels)
     assert _same_bits(dev.log_weights, host.log_weights)
     assert np.array_equal(dev.batch.scores, host.batch.scores)
+    assert np.array_equal(dev.max_sampling_id, host.max_sampling_id) and dev.max_sampling_id.dtype == np.float32
+    assert _same_bits(dev.lse_pos, host.lse_pos) and _same_bits(dev.lse_neg, host.lse_neg)
+    assert np.array_equal(dev.raw_scores["dense"], host.raw_scores["dense"])
     assert dev.batch.labels[:, :2].all()
+    # no gold ids, deterministic top-`total` (temperature 0), device-resident fp16-free torch queries
+    import torch
+
+    host0 = vod_b200.sample_search_results(search_results=vod_b200.RetrievalBatch(scores=s, indices=i, labels=None),
+                                           raw_scores={"dense": s}, total=8, max_pos_sections=3, temperature=0.0, seed=1)
+    pipe0 = vod_b200.DenseRetrievalSampler(st, top_k=1000, total=8, max_pos_sections=3, mode="tensor", temperature=0.0)
+    dev0 = pipe0(torch.from_numpy(xq).cuda(), seed=1)
+    assert np.array_equal(dev0.batch.indices, host0.batch.indices) and _same_bits(dev0.log_weights, host0.log_weights)
+    assert np.array_equal(dev0.max_sampling_id, host0.max_sampling_id)
+    assert np.array_equal(pipe0.last_local_ids, np.tile(np.arange(8), (B, 1)))
+    st.close()
+
+
+def test_chain_with_fewer_rows_than_picks_wraps_like_numpy():
+    """total > finite candidates: unused sampler slots (-1) gather the last retrieved column, as
+    np.take_along_axis does in the reference (core/sample.py:57-58); max_sampling_id counts finite negatives."""
+    from tests.helpers import int_valued
+
+    rng = np.random.default_rng(3)
+    st = vod_b200.CorpusStore(5, 64, dtype="float32")
+    st.add(int_valued(rng, (5, 64)))
+    xq = int_valued(rng, (3, 64))
+    s, i = st.search(xq, 8, mode="exact")
+    gold = i[:, :1].copy()
+    labels = (i[:, :, None] == gold[:, None, :]).any(-1).astype(np.int64)
+    host = vod_b200.sample_search_results(search_results=vod_b200.RetrievalBatch(scores=s, indices=i, labels=labels),
+                                          raw_scores={"dense": s}, total=8, max_pos_sections=2, seed=9, offset=1)
+    dev = vod_b200.DenseRetrievalSampler(st, top_k=8, total=8, max_pos_sections=2, mode="exact")(xq, gold, seed=9, offset=1)
+    assert np.array_equal(dev.batch.indices, host.batch.indices)
+    assert np.array_equal(dev.batch.scores, host.batch.scores)
+    assert np.array_equal(dev.batch.labels, host.batch.labels)
+    assert _same_bits(dev.log_weights, host.log_weights)
+    assert np.array_equal(dev.max_sampling_id, host.max_sampling_id)
+    with pytest.raises(ValueError):
+        vod_b200.DenseRetrievalSampler(st, top_k=8, total=4, max_pos_sections=5)(xq)
     st.close()

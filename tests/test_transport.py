@@ -62,3 +62,54 @@ def test_client_without_master_or_address_fails_loudly():
     c2 = pickle.loads(pickle.dumps(B200SearchClient(master_id=999, pid=-1)))
     with pytest.raises(vod_b200.VodbError):
         c2.search(vector=np.zeros((1, 8), np.float32), top_k=3)
+
+
+@pytest.mark.timeout(60)
+def test_concurrent_requests_share_scans():
+    """Requests that queue up while a scan runs are served by ONE following scan, each caller gets its own rows."""
+    import threading
+    import time
+
+    from vod_b200.transport import ScanCoalescer
+
+    seen = []
+
+    def slow_search(vectors, top_k, mode):
+        seen.append(len(vectors))
+        time.sleep(0.05)
+        return _fake_search(vectors, top_k, mode)
+
+    co = ScanCoalescer(slow_search, max_queries=64)
+    results = {}
+
+    def caller(t):
+        v = np.full((3 + t % 2, 8), float(t), np.float32)
+        k = 5 if t != 6 else 7                       # one request with another top_k: never batched with the rest
+        results[t] = (v, k, co.submit(v, k, "tensor"))
+
+    threads = [threading.Thread(target=caller, args=(t,)) for t in range(10)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    co.close()
+    assert co.n_requests == 10 and co.n_scans < 10 and max(seen) > 4
+    for t, (v, k, (s, i)) in results.items():
+        exp_s, exp_i = _fake_search(v, k, "tensor")
+        assert np.array_equal(s, exp_s) and np.array_equal(i, exp_i) and s.flags.writeable
+    with pytest.raises(ValueError):
+        ScanCoalescer(slow_search).submit(np.zeros(8, np.float32), 3, None)
+    with pytest.raises(RuntimeError):
+        co.submit(np.zeros((1, 8), np.float32), 3, None)
+
+
+@pytest.mark.timeout(60)
+def test_failed_scan_reaches_every_waiter_and_server_keeps_running():
+    from vod_b200.transport import ScanCoalescer
+
+    co = ScanCoalescer(_fake_search)
+    with pytest.raises(ValueError, match="query dimension 3"):
+        co.submit(np.ones((2, 3), np.float32), 2, None)
+    s, i = co.submit(np.ones((2, 8), np.float32), 2, None)
+    assert s.shape == (2, 2) and i.shape == (2, 2)
+    co.close()

@@ -18,7 +18,7 @@ PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "_build"
 LIB = PKG / "libvodb.so"
-SOURCES = ["api.cu", "select.cu", "score_exact.cu", "score_tc.cu", "sample.cu", "merge_results.cu"]
+SOURCES = ["api.cu", "select.cu", "score_exact.cu", "score_tc.cu", "sample.cu", "merge_results.cu", "chain.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

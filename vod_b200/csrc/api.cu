@@ -364,8 +364,9 @@ int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes) {
 void free_workspace(Workspace& w) {
   cudaFree(w.cand_s); cudaFree(w.cand_i); cudaFree(w.cnt); cudaFree(w.tau); cudaFree(w.overflow);
   if (w.overflow_host) cudaFreeHost(w.overflow_host);
-  cudaFree(w.q_stage); cudaFree(w.q_in); cudaFree(w.out_pack);
+  cudaFree(w.q_stage); cudaFree(w.q_in); cudaFree(w.out_pack); cudaFree(w.chain_dev);
   if (w.out_host) cudaFreeHost(w.out_host);
+  if (w.chain_host) cudaFreeHost(w.chain_host);
   w = Workspace();
 }
 
@@ -1052,6 +1053,106 @@ int vodb_sample(int device, const float* scores, const uint8_t* labels, const fl
     return VODB_ECUDA;
   }
   return rc;
+}
+
+// The RealmCollate chain for the dense-only flow in ONE call (realm_collate.py:101-122 -> core/sample.py:22-84):
+// search top_k -> label the retrieved ids against the gold ids -> labeled priority sampling of k_total ->
+// gather ids / scores at the picks + max_sampling_id. Only the [nq, k_total] result crosses PCIe (one packed copy).
+int vodb_retrieve_sample(vodb_store* s, const void* queries, int q_dtype, int q_on_device, int nq, int top_k, int mode,
+                         const int64_t* gold_ids, int n_gold, int k_positive, int k_total, float temperature,
+                         int max_support, int quirks, uint64_t seed, uint64_t offset, int64_t* out_idx,
+                         float* out_scores, float* out_logw, uint8_t* out_labels, float* out_lse, float* out_msid,
+                         int64_t* out_local, void* stream) {
+  int rc = check_search_args(s, queries, q_dtype, nq, top_k, mode, out_scores, out_idx, "vodb_retrieve_sample");
+  if (rc != VODB_OK) return rc;
+  VODB_REQUIRE(top_k <= 8192, "vodb_retrieve_sample: top_k=%d > 8192", top_k);
+  VODB_REQUIRE(k_total >= 0 && k_positive >= 0 && k_positive <= k_total,
+               "vodb_retrieve_sample: need 0 <= k_positive <= k_total (got %d, %d)", k_positive, k_total);
+  VODB_REQUIRE(n_gold >= 0 && (n_gold == 0 || gold_ids != nullptr), "vodb_retrieve_sample: gold_ids is NULL");
+  if (nq == 0) return VODB_OK;
+  VODB_REQUIRE(out_logw && out_labels && out_lse && out_msid, "vodb_retrieve_sample: output pointer is NULL");
+  if (s->n_added <= 0) {
+    set_error("vodb_retrieve_sample: the store is empty");
+    return VODB_ESTATE;
+  }
+  if (is_tensor_mode(mode) && !tensor_path_supported(s)) {
+    set_error("vodb_retrieve_sample: VODB_MODE_TENSOR* needs a bf16/f16 store and a driver exporting cuTensorMapEncodeTiled");
+    return VODB_EUNSUPPORTED;
+  }
+  DeviceGuard guard(s->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  rc = ensure_workspace(s, nq, top_k, dtype_size(q_dtype));
+  if (rc != VODB_OK) return rc;
+  Workspace& w = s->ws;
+
+  // chain scratch: [result pack: idx i64 | local i64 | scores f32 | logw f32 | lse f32 x2 | msid f32 | overflow | labels u8]
+  // followed by device-only parts [gold ids i64 | retrieved labels u8]
+  const size_t nkt = (size_t)nq * k_total, nK = (size_t)nq * top_k;
+  const size_t o_idx = 0, o_local = o_idx + nkt * 8, o_scores = o_local + nkt * 8, o_logw = o_scores + nkt * 4;
+  const size_t o_lse = o_logw + nkt * 4, o_msid = o_lse + (size_t)nq * 8, o_flag = o_msid + (size_t)nq * 4;
+  const size_t o_olab = o_flag + 4, pack_bytes = o_olab + nkt;
+  const size_t o_gold = (pack_bytes + 7) / 8 * 8, o_labels = o_gold + (size_t)nq * n_gold * 8, need = o_labels + nK + 16;
+  if (need > w.chain_bytes) {
+    if (w.chain_dev) cudaFree(w.chain_dev);
+    if (w.chain_host) cudaFreeHost(w.chain_host);
+    w.chain_dev = nullptr; w.chain_host = nullptr; w.chain_bytes = 0;
+    VODB_CUDA_CHECK(cudaMalloc(&w.chain_dev, need));
+    VODB_CUDA_CHECK(cudaMallocHost(&w.chain_host, need));
+    w.chain_bytes = need;
+  }
+  char* d = w.chain_dev;
+  const void* q_dev = nullptr;
+  rc = upload_queries(s, queries, q_dtype, q_on_device, nq, st, &q_dev);
+  if (rc != VODB_OK) return rc;
+  uint8_t* labels = nullptr;
+  if (n_gold > 0) {
+    std::memcpy(w.chain_host + o_gold, gold_ids, (size_t)nq * n_gold * 8);  // pinned staging: the copy below is async
+    VODB_CUDA_CHECK(cudaMemcpyAsync(d + o_gold, w.chain_host + o_gold, (size_t)nq * n_gold * 8, cudaMemcpyHostToDevice, st));
+    labels = reinterpret_cast<uint8_t*>(d + o_labels);
+  }
+  int64_t* top_i = reinterpret_cast<int64_t*>(w.out_pack);
+  float* top_s = reinterpret_cast<float*>(w.out_pack + nK * 8);
+  int max_sup = max_support;
+  if (max_sup >= 0 && max_sup < k_total) max_sup = k_total;  // sample.py:133-135
+
+  bool safe = false;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    rc = run_scan(s, q_dev, q_dtype, nq, top_k, mode, safe, top_s, top_i, st);
+    if (rc != VODB_OK) return rc;
+    if (labels) {
+      rc = launch_match_labels(top_i, reinterpret_cast<const int64_t*>(d + o_gold), n_gold, nq, top_k, labels, st);
+      if (rc != VODB_OK) return rc;
+    }
+    rc = launch_sample(top_s, labels, nullptr, nq, top_k, k_positive, k_total, /*normalized=*/1, temperature, max_sup,
+                       quirks, seed, offset, reinterpret_cast<int64_t*>(d + o_local), reinterpret_cast<float*>(d + o_logw),
+                       reinterpret_cast<uint8_t*>(d + o_olab), reinterpret_cast<float*>(d + o_lse), st);
+    if (rc != VODB_OK) return rc;
+    rc = launch_gather_picks(top_s, top_i, labels, nq, top_k, k_total, reinterpret_cast<const int64_t*>(d + o_local),
+                             reinterpret_cast<const uint8_t*>(d + o_olab), reinterpret_cast<int64_t*>(d + o_idx),
+                             reinterpret_cast<float*>(d + o_scores), reinterpret_cast<float*>(d + o_msid), st);
+    if (rc != VODB_OK) return rc;
+    VODB_CUDA_CHECK(cudaMemcpyAsync(d + o_flag, w.overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    VODB_CUDA_CHECK(cudaMemcpyAsync(w.chain_host, d, pack_bytes, cudaMemcpyDeviceToHost, st));
+    VODB_CUDA_CHECK(cudaStreamSynchronize(st));
+    int flag;
+    std::memcpy(&flag, w.chain_host + o_flag, sizeof(int));
+    if (flag == 0) break;
+    VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
+    if (safe) {
+      set_error("vodb_retrieve_sample: candidate list overflow in safe mode (internal error)");
+      return VODB_ESTATE;
+    }
+    safe = true;
+  }
+  const char* h = w.chain_host;
+  std::memcpy(out_idx, h + o_idx, nkt * 8);
+  if (out_local) std::memcpy(out_local, h + o_local, nkt * 8);
+  std::memcpy(out_scores, h + o_scores, nkt * 4);
+  std::memcpy(out_logw, h + o_logw, nkt * 4);
+  std::memcpy(out_lse, h + o_lse, (size_t)nq * 8);
+  std::memcpy(out_msid, h + o_msid, (size_t)nq * 4);
+  std::memcpy(out_labels, h + o_olab, nkt);
+  return VODB_OK;
 }
 
 }  // extern "C"

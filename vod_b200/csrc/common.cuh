@@ -122,6 +122,10 @@ struct Workspace {
   char* out_pack = nullptr;
   char* out_host = nullptr;  // pinned
   size_t out_cap = 0;        // elements (nq * k) the pack can hold
+  // retrieve -> sample chain (vodb_retrieve_sample): labels / gold ids / sampler outputs / packed result + pinned mirror
+  char* chain_dev = nullptr;
+  char* chain_host = nullptr;  // pinned
+  size_t chain_bytes = 0;
 };
 
 }  // namespace vodb
@@ -217,5 +221,11 @@ int launch_sample(const float* scores, const uint8_t* labels, const float* noise
                   int k_total, int normalized, float temperature, int max_support, int quirks, uint64_t seed,
                   uint64_t offset, int64_t* out_ids, float* out_logw, uint8_t* out_labels, float* out_lse,
                   cudaStream_t stream);
+
+int launch_match_labels(const int64_t* idx, const int64_t* gold, int n_gold, int B, int K, uint8_t* labels,
+                        cudaStream_t stream);
+int launch_gather_picks(const float* scores, const int64_t* idx, const uint8_t* labels, int B, int K, int k_total,
+                        const int64_t* local, const uint8_t* picked_labels, int64_t* out_idx, float* out_scores,
+                        float* out_msid, cudaStream_t stream);
 
 }  // namespace vodb
