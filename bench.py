@@ -135,50 +135,67 @@ def make_queries(torch, n_batches: int, nq: int, device, store_dtype):
     return q.to(store_dtype).to(torch.float32).to(device)
 
 
-def worker_clients_section(vod_b200, store, torch, n_workers: int = 8, n_batches: int = 12):
-    """configs[3] as the DataLoader sees it: `n_workers` clients, each holding its own Unix-socket connection to the
-    GPU-owning master (like the reference's forkserver workers holding a FaissClient, src/vod_exps/train.py:15),
-    each issuing 32-query top-1000 searches back to back. Requests that queue up during a scan share the next scan
-    (vod_b200/transport.py ScanCoalescer); the uncoalesced line is the one-request-per-scan behaviour of the
-    reference's single uvicorn worker (server.py:98). Threads stand in for worker processes: the socket path and the
-    server are the same, and this keeps the bench free of forked CUDA state."""
-    import threading
+_WORKER_CODE = """
+import pickle, sys, time
+import numpy as np
+from vod_b200.transport import RemoteSearch
+address, authkey, n_batches, seed = pickle.loads(bytes.fromhex(sys.argv[1]))
+v = np.random.default_rng(seed).standard_normal((32, 768), dtype=np.float32)
+c = RemoteSearch(address, authkey)
+c.search(v, 1000, None)                      # connect + warm
+print("ready", flush=True)
+sys.stdin.readline()                          # start signal
+t0 = time.perf_counter()
+for _ in range(n_batches):
+    s, i = c.search(v, 1000, None)
+assert s.shape == (32, 1000) and i.shape == (32, 1000) and (i >= 0).all()
+print(time.perf_counter() - t0, flush=True)
+"""
 
-    from vod_b200.transport import RemoteSearch, SearchServer
 
-    q = make_queries(torch, n_workers, 32, "cpu", torch.float32).numpy()
+def worker_clients_section(store, n_workers: int = 8, n_batches: int = 12):
+    """configs[3] as the DataLoader sees it: `n_workers` worker PROCESSES, each holding its own Unix-socket
+    connection to the GPU-owning master (like the reference's forkserver workers holding a FaissClient,
+    src/vod_exps/train.py:15), each issuing 32-query top-1000 searches back to back. Requests that queue up during a
+    scan share the next scan (vod_b200/transport.py ScanCoalescer); the uncoalesced line is the
+    one-request-per-scan behaviour of the reference's single uvicorn worker (server.py:98)."""
+    import pickle
+
+    from vod_b200.transport import SearchServer
+
     out = {"workers": n_workers, "queries_per_request": 32, "top_k": 1000, "requests_per_worker": n_batches, "unit": "queries/s"}
+    root = str(pathlib.Path(__file__).resolve().parent)
     for label, coalesce in (("coalesced", True), ("one_scan_per_request", False)):
         server = SearchServer(lambda v, k, mode: store.search(v, k, mode=mode or "tensor3"), lambda: True, coalesce=coalesce)
         server.start()
+        procs = []
         try:
-            clients = [RemoteSearch(server.address, server.authkey) for _ in range(n_workers)]
-            for c, v in zip(clients, q):
-                c.search(v, 1000, None)  # connect + warm
-            errors = []
-
-            def work(c, v):
-                try:
-                    for _ in range(n_batches):
-                        c.search(v, 1000, None)
-                except Exception as exc:  # noqa: BLE001
-                    errors.append(exc)
-
-            threads = [threading.Thread(target=work, args=(c, v)) for c, v in zip(clients, q)]
+            for w in range(n_workers):
+                arg = pickle.dumps((server.address, server.authkey, n_batches, w)).hex()
+                procs.append(subprocess.Popen([sys.executable, "-c", _WORKER_CODE, arg], stdin=subprocess.PIPE,
+                                              stdout=subprocess.PIPE, text=True, cwd=root))
+            for p in procs:
+                if p.stdout.readline().strip() != "ready":
+                    raise RuntimeError("search worker failed to start")
             scans0 = server.coalescer.n_scans if server.coalescer else 0
             t0 = time.perf_counter()
-            for th in threads:
-                th.start()
-            for th in threads:
-                th.join()
+            for p in procs:
+                p.stdin.write("go\n")
+                p.stdin.flush()
+            for p in procs:
+                float(p.stdout.readline())
             dt = time.perf_counter() - t0
-            if errors:
-                raise errors[0]
             out[label] = n_workers * n_batches * 32 / dt
             if server.coalescer:
                 out["scans_issued"] = server.coalescer.n_scans - scans0
                 out["requests_served"] = n_workers * n_batches
         finally:
+            for p in procs:
+                try:
+                    p.stdin.close()
+                    p.wait(timeout=30)
+                except Exception:  # noqa: BLE001
+                    p.kill()
             server.stop()
     return out
 
@@ -388,7 +405,7 @@ def main():
                                    "(host queries in, [32,8] picks + log-weights out, one D2H)",
                        "chain_ms_p50": times[len(times) // 2], "chain_ms_p90": times[(len(times) * 9) // 10],
                        "sampler_kernel_us_p50": samp[len(samp) // 2]}
-            config4["dataloader_workers"] = worker_clients_section(vod_b200, corpus.store, torch)
+            config4["dataloader_workers"] = worker_clients_section(corpus.store)
         except Exception as exc:
             config4 = {"error": f"{type(exc).__name__}: {exc}"}
 
