@@ -5,7 +5,7 @@ def bench(name): return json.loads((P / name).read_text().strip().splitlines()[-
 out = []; A = out.append
 A("# Round 1 — profile summary (B200, sm_100a)\n")
 A("All numbers from `gpurun` boxes (1x B200 unless noted). Peaks: `MEASURED_PEAKS.json` — HBM 6534.8 GB/s (copy kernel), bf16 1671.7 TFLOP/s burst / 1404.1 sustained (cuBLAS). Workload: BASELINE configs[1], 10M x 768 bf16, exact top-100. Box-to-box variation of the same build is about +-4% (2.19-2.29 ms for the 64-query step).\n")
-A("Files: `r01a_*` first working tcgen05 path; `r01b_*` dump mode + staged survivors; `r01c..g_*` bench lines along the way; `r01h_*` final state of the round (launch list, `ncu --set full` raw pages of `score_tc_kernel<64,1>` and the 2-CTA `score_tc2_kernel`, bench lines of both arms); `r01i_*` final multi-GPU bench lines; probes: `r01_schedule_sweep.jsonl`, `r01_query_terms_probe.json`, `r01_configs_3_5_probe.json`, `r01_compute_sanitizer.txt`. Regenerate this file with `python scripts/make_profile_summary.py`.\n")
+A("Files: `r01a_*` first working tcgen05 path; `r01b_*` dump mode + staged survivors; `r01c..g_*` bench lines along the way; `r01h_*` final state of the round (launch list, `ncu --set full` raw pages of `score_tc_kernel<64,1>` and the 2-CTA `score_tc2_kernel`, bench lines of both arms); `r01i_*` multi-GPU bench lines with the flag/fence exchange; `r01j_*` final bench lines of the round (1 GPU both arms, 2/4/8 GPUs with the epoch-tagged LL exchange, 8 GPUs NCCL); probes: `r01_schedule_sweep.jsonl`, `r01_query_terms_probe.json`, `r01_configs_3_5_probe.json`, `r01_compute_sanitizer.txt`. Regenerate this file with `python scripts/make_profile_summary.py`.\n")
 d = bench("r01h_bench.json"); f = bench("r01f_bench.json")
 A("## Headline (r01h_bench.json; r01f_bench.json is the same build on another box)\n")
 A("| quantity | r01h | r01f |\n|---|---|---|")
@@ -26,7 +26,8 @@ A(f"| clocks during the timed region | {d['clocks']} | |\n")
 A("## Strong scaling, same 10M-row corpus (queries/s, 64-query batches)\n")
 A("| GPUs | exchange | file | queries/s | ms/step | vs 1 GPU of the same series | 8192-query batch q/s |\n|---|---|---|---|---|---|---|")
 series = [("early (before select/PDL work)", [(1, 'r01c_bench.json'), (2, 'r01c_bench_n2_p2p.json'), (2, 'r01c_bench_n2_nccl.json'), (4, 'r01d_bench_n4_p2p.json'), (8, 'r01d_bench_n8_p2p.json'), (8, 'r01d_bench_n8_nccl.json')]),
-          ("final", [(1, 'r01h_bench.json'), (2, 'r01i_bench_n2_p2p.json'), (4, 'r01i_bench_n4_p2p.json'), (8, 'r01i_bench_n8_p2p.json'), (8, 'r01i_bench_n8_nccl.json')])]
+          ("flag + fence exchange", [(1, 'r01h_bench.json'), (2, 'r01i_bench_n2_p2p.json'), (4, 'r01i_bench_n4_p2p.json'), (8, 'r01i_bench_n8_p2p.json'), (8, 'r01i_bench_n8_nccl.json')]),
+          ("final (epoch-tagged LL exchange)", [(1, 'r01j_bench.json'), (2, 'r01j_bench_n2_p2p.json'), (4, 'r01j_bench_n4_p2p.json'), (8, 'r01j_bench_n8_p2p.json'), (8, 'r01j_bench_n8_nccl.json')])]
 for label, files in series:
     base = None
     for n, fn in files:
@@ -46,7 +47,7 @@ A("## One 64-query search, per launch (ncu launch list r01h_launches_ncu.csv: co
 A("| # | kernel | grid x block | us |\n|---|---|---|---|")
 tot = sc = 0
 for row in r[start:start + 9]:
-    name = row['Kernel Name']; short = name.split('>::')[-1].split('(')[0]
+    name = row['Kernel Name']; short = name.split('<unnamed>::', 1)[-1].split('(')[0]
     us = float(row['Metric Value']) / 1e3; tot += us
     if 'score_tc' in short: sc += us
     A(f"| {row['ID']} | `{short}` | {row['Grid Size']} x {row['Block Size']} | {us:.1f} |")
