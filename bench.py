@@ -51,6 +51,9 @@ def parse_args():
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     p.add_argument("--large-steps", type=int, default=3)
     p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="cross-shard exchange (N>1)")
+    p.add_argument("--top-k", type=int, default=TOP_K, help="results per query (BASELINE configs[2] uses 1000)")
+    p.add_argument("--store-dtype", default="bfloat16", choices=["bfloat16", "float16"],
+                   help="dtype of the HBM store (BASELINE configs[2] uses float16)")
     return p.parse_args()
 
 
@@ -228,7 +231,7 @@ def run_reference(args):
     sample = (f"{rows} of {args.rows} rows x {DIM} fp32 scanned per step (numpy/OpenBLAS sgemm + exact top-{TOP_K}), "
               f"time scaled x{scale:.0f} (a flat scan is linear in rows)")
     line = {
-        "impl": "reference", "metric": "mips_top100_queries_per_sec", "value": value, "unit": "queries/s",
+        "impl": "reference", "metric": f"mips_top{TOP_K}_queries_per_sec", "value": value, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, mode="cpu"),
@@ -239,19 +242,24 @@ def run_reference(args):
 
 
 def workload_config(args, mode):
+    short = {"bfloat16": "bf16", "float16": "fp16"}[args.store_dtype]
     return {
-        "workload": f"BASELINE configs[1]: exact MIPS top-{TOP_K}, {args.rows} x {DIM} bf16 corpus, {Q_SMALL}-query batches",
-        "rows": args.rows, "dim": DIM, "store_dtype": "bf16", "queries_per_batch": Q_SMALL, "top_k": TOP_K,
+        "workload": (f"BASELINE configs[{1 if short == 'bf16' and TOP_K == 100 else 2}]: exact MIPS top-{TOP_K}, {args.rows} x {DIM} "
+                     f"{short} corpus, {Q_SMALL}-query batches"),
+        "rows": args.rows, "dim": DIM, "store_dtype": short, "queries_per_batch": Q_SMALL, "top_k": TOP_K,
         "mode": mode,
         "sharding": (f"rows split over {args.gpus} ranks; exchange={getattr(args, 'exchange', 'p2p')} "
-                     "(p2p = final select stores into peer-mapped buffers + flag, merge kernel waits; nccl = all-gather + merge)")
+                     "(p2p = final select stores epoch-tagged words into peer-mapped buffers, merge kernel waits on the tags; "
+                     "nccl = all-gather + merge)")
         if args.gpus > 1 else "single shard",
         "l2": "inputs larger than L2: the corpus shard streamed every step is >= 1.9 GB (L2 = 126 MB); fresh queries per step",
     }
 
 
 def main():
+    global TOP_K
     args = parse_args()
+    TOP_K = args.top_k
     if args.impl == "reference":
         run_reference(args)
         return
@@ -285,7 +293,8 @@ def main():
         return float(t.item())
 
     # ---- corpus: row shard of the global synthetic corpus, generated on the device ----
-    corpus = vod_b200.ShardedCorpus(args.rows, DIM, dtype="bfloat16", device=local_rank, rank=rank, world_size=world,
+    tdtype = {"bfloat16": torch.bfloat16, "float16": torch.float16}[args.store_dtype]
+    corpus = vod_b200.ShardedCorpus(args.rows, DIM, dtype=args.store_dtype, device=local_rank, rank=rank, world_size=world,
                                     exchange=args.exchange, max_queries=Q_LARGE, max_k=TOP_K)
     corpus.fill_synthetic(CORPUS_SEED)
     torch.cuda.synchronize()
@@ -293,7 +302,7 @@ def main():
     shard_bytes = shard_rows * DIM * 2
 
     def timed_section(nq: int, steps: int, warmup: int, sample_clocks: bool):
-        queries = make_queries(torch, warmup + steps, nq, dev, torch.bfloat16)
+        queries = make_queries(torch, warmup + steps, nq, dev, tdtype)
         for i in range(warmup):
             corpus.search_device(queries[i], TOP_K, mode="tensor")
         torch.cuda.synchronize()
@@ -338,7 +347,7 @@ def main():
     }
 
     # ---- e2e: reference-facing client call with host buffers (pinned H2D + D2H inside the timed region) ----
-    q_host = make_queries(torch, args.warmup + args.steps, Q_SMALL, "cpu", torch.bfloat16).pin_memory()
+    q_host = make_queries(torch, args.warmup + args.steps, Q_SMALL, "cpu", tdtype).pin_memory()
     if world == 1:
         master = vod_b200.B200SearchMaster(store=corpus.store, mode="tensor")
         master.__enter__()
@@ -366,7 +375,7 @@ def main():
            else "ShardedCorpus.search_device on pinned host queries + .cpu() of the merged result"}
 
     # ---- per-call latency (search enqueue -> results ready on the device), p10 / p50 / p90 over fresh batches ----
-    lat_q = make_queries(torch, 40, Q_SMALL, dev, torch.bfloat16)
+    lat_q = make_queries(torch, 40, Q_SMALL, dev, tdtype)
     lat = []
     for i in range(40):
         barrier()
@@ -458,10 +467,11 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": "mips_top100_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world,
+            "metric": f"mips_top{TOP_K}_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(args, mode="tensor (tcgen05, bf16 inputs, fp32 accumulate)"),
+            "scaling": "strong", "vs_baseline": None, "dtype": {"bfloat16": "bf16", "float16": "fp16"}[args.store_dtype],
+            "data": "synthetic",
+            "config": workload_config(args, mode=f"tensor (tcgen05, {args.store_dtype} inputs, fp32 accumulate)"),
             "corpus_gb_per_s": args.rows * DIM * 2 / (ms_step * 1e-3) / 1e9,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step, "segments": int(stats["segments"]), "cap": int(stats["cap"]),

@@ -30,6 +30,9 @@ if [[ $STEP == all || $STEP == ncu ]]; then
   run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:score_tc_kernel -s 4 -c 4 -o gpurun_out/prof_score_tc python bench.py --steps 2 --warmup 1 --no-cpu --no-large
   run ncu_full256 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:score_tc2_kernel -s 7 -c 7 -o gpurun_out/prof_score_tc256 python bench.py --steps 1 --warmup 1 --no-cpu --large-steps 1
 fi
+if [[ $STEP == all || $STEP == ncu_aux ]]; then
+  run ncu_aux 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:score_exact|select_kernel|merge|sample_kernel|match_labels|gather_picks' -c 60 -o gpurun_out/prof_aux python scripts/ncu_aux_probe.py
+fi
 if [[ $STEP == all || $STEP == sanitizer ]]; then
   run sanitizer_memcheck 600 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitizer_probe.py
   run sanitizer_racecheck 600 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/sanitizer_probe.py small

@@ -1,11 +1,11 @@
 """Builds profiles/r01_summary.md from the committed captures (bench lines, ncu launch list, ncu raw pages)."""
 import csv, json, pathlib
 P = pathlib.Path(__file__).resolve().parents[1] / "profiles"
-def bench(name): return json.loads((P / name).read_text().strip().splitlines()[-1])
+def bench(name): return json.loads([l for l in (P / name).read_text().splitlines() if l.startswith('{')][-1])
 out = []; A = out.append
 A("# Round 1 — profile summary (B200, sm_100a)\n")
 A("All numbers from `gpurun` boxes (1x B200 unless noted). Peaks: `MEASURED_PEAKS.json` — HBM 6534.8 GB/s (copy kernel), bf16 1671.7 TFLOP/s burst / 1404.1 sustained (cuBLAS). Workload: BASELINE configs[1], 10M x 768 bf16, exact top-100. Box-to-box variation of the same build is about +-4% (2.19-2.29 ms for the 64-query step).\n")
-A("Files: `r01a_*` first working tcgen05 path; `r01b_*` dump mode + staged survivors; `r01c..g_*` bench lines along the way; `r01h_*` final state of the round (launch list, `ncu --set full` raw pages of `score_tc_kernel<64,1>` and the 2-CTA `score_tc2_kernel`, bench lines of both arms); `r01i_*` multi-GPU bench lines with the flag/fence exchange; `r01j_*` final bench lines of the round (1 GPU both arms, 2/4/8 GPUs with the epoch-tagged LL exchange, 8 GPUs NCCL); probes: `r01_schedule_sweep.jsonl`, `r01_query_terms_probe.json`, `r01_configs_3_5_probe.json`, `r01_compute_sanitizer.txt`. Regenerate this file with `python scripts/make_profile_summary.py`.\n")
+A("Files: `r01a_*` first working tcgen05 path; `r01b_*` dump mode + staged survivors; `r01c..g_*` bench lines along the way; `r01h_*` final state of the round (launch list, `ncu --set full` raw pages of `score_tc_kernel<64,1>` and the 2-CTA `score_tc2_kernel`, bench lines of both arms); `r01i_*` multi-GPU bench lines with the flag/fence exchange; `r01j_*` final bench lines of the round (1 GPU both arms, 2/4/8 GPUs with the epoch-tagged LL exchange, 8 GPUs NCCL); `r01k_*` BASELINE configs[2] at full size (100M x 768 fp16 over 2/4/8 GPUs, top-1000), `ncu --set full` raw page of the kernels beside the tensor-core scan, latency probe; probes: `r01_schedule_sweep.jsonl`, `r01_query_terms_probe.json`, `r01_configs_3_5_probe.json`, `r01_compute_sanitizer.txt`. Regenerate this file with `python scripts/make_profile_summary.py`.\n")
 d = bench("r01h_bench.json"); f = bench("r01f_bench.json")
 A("## Headline (r01h_bench.json; r01f_bench.json is the same build on another box)\n")
 A("| quantity | r01h | r01f |\n|---|---|---|")
@@ -65,6 +65,36 @@ table('r01h_score_tc64_ncu_raw.csv', "ncu --set full, `score_tc_kernel<64,1>` (6
 A("DRAM traffic equals the algorithmic bytes (15.36 GB read per search, +0.07%): nothing is re-read, the score matrix never exists. The two large segments run at 6.9-7.0 TB/s (84-85% of ncu's DRAM peak, 106% of the copy-kernel figure) with the tensor pipe 16-20% busy: HBM-bound as designed. 128 registers, 1 CTA/SM, 192 threads.\n")
 table('r01h_score_tc2_pair_ncu_raw.csv', "ncu --set full, `score_tc2_kernel` (2-CTA pairs, 8192 queries), the 7 segments of one search", [4096, 12288, 49152, 196608, 786432, 3145728, 5805696])
 A("The large segments keep the tensor pipe 83-87% active at 1.41-1.44 GHz (sw_power_cap): the kernel sits at the MMA issue limit at the clock the 1 kW budget allows. Against the 1-CTA capture (`r01e_score_tc256_ncu_raw.csv`: 86-90% active at 1.38 GHz, L2 throughput 67-72%) the pair kernel moves 1/3 less data per flop (L2 throughput 50%), which buys the higher clock. Early segments (dense survivors, few items per pair) are below that; they cover 10% of the rows.\n")
+A("## BASELINE configs[2] at full size: 100M x 768 fp16 row-sharded over 2/4/8 B200, top-1000, fused peer-memory exchange (r01k_bench_c3_n*_p2p.json)\n")
+A("The north-star target configuration (>= 80% of the HBM roofline at 64-query batches, >= 60% of the bf16 tensor roofline at 8192-query batches). `python -m torch.distributed.run --nproc-per-node N bench.py --gpus N --rows 100000000 --top-k 1000 --store-dtype float16`.\n")
+A("| GPUs | 64-query: queries/s (ms/step) | aggregate corpus GB/s | scoring kernels, % of measured HBM peak | whole step, % | p50 latency ms | 8192-query: queries/s (ms/step) | scoring kernels TFLOP/s per GPU (% of burst / sustained peak) | whole step, % of burst |\n|---|---|---|---|---|---|---|---|---|")
+for n in (2, 4, 8):
+    x = bench(f"r01k_bench_c3_n{n}_p2p.json"); r = x['roofline']; L = x['large_batch']; R = L['roofline']
+    A(f"| {n} | {x['value']:.0f} ({x['ms_per_step']:.3f}) | {x['corpus_gb_per_s']:.0f} | {r['frac']*100:.1f} | {r['whole_step_frac']*100:.1f} | {x['latency']['p50']:.3f} | {L['value']:.0f} ({L['ms_per_step']:.1f}) | {R['achieved']:.0f} ({R['frac']*100:.1f} / {R['frac_of_sustained']*100:.1f}) | {R['whole_step_frac']*100:.1f} |")
+A("\nPer-kernel times come from a separate pass with events around every launch (idle gaps between kernels); the whole-step numbers are the back-to-back timed region, where the 1 kW power cap holds the clocks lower (`sw_power_cap` in every run) — that, the selects (k = 1000: 4-8 ms per 8192-query batch) and the merge are the difference between the two columns.\n")
+lp = json.loads((P / 'r01k_latency_probe.json').read_text())
+A("## Isolated-call latency vs submission pattern (r01k_latency_probe.json, scripts/latency_probe.py; 10M x 768 bf16, 64 queries)\n")
+A("| pattern | ms per search (p10 / p50 / p90) |\n|---|---|")
+A(f"| 40 searches back to back, one event pair | {lp['back_to_back_ms']:.3f} (mean) |")
+for key, label in (("isolated", "one search per synchronize, no pause"), ("isolated_gap_5ms", "one search per synchronize, 5 ms idle between calls"), ("isolated_gap_50ms", "one search per synchronize, 50 ms idle between calls"), ("pairs", "two searches per synchronize"), ("quads", "four searches per synchronize")):
+    c = lp[key]['call_ms']; A(f"| {label} | {c['p10']:.3f} / {c['p50']:.3f} / {c['p90']:.3f} |")
+A(f"| host time to enqueue one search (9 launches) | {lp['host_enqueue_ms']['p50']*1e3:.0f} us |")
+A("\nThe same kernels take 2.19 ms (7.0 TB/s) when the GPU idles a few ms between searches - the situation inside a training loop - and 2.30-2.45 ms under a saturating stream: the step time is set by the board's power / thermal management of HBM + tensor work, not by launch structure (enqueue is 36 us, selects 60 us).\n")
+rows = list(csv.reader(open(P / 'r01k_aux_kernels_ncu_raw.csv'))); hdr = rows[0]; ix = {h: i for i, h in enumerate(hdr)}
+A("## Kernels beside the tensor-core scan (ncu --set full, r01k_aux_kernels_ncu_raw.csv, scripts/ncu_aux_probe.py)\n")
+A("| kernel | grid x block | us | DRAM read MB | regs | warps active % | FMA pipe active % | what it ran |\n|---|---|---|---|---|---|---|---|")
+what = {"score_exact_kernel": "fp32-exact scan, 64 queries over 1M x 768 fp32 (3 segments)", "select_kernel": "radix select + sort of the candidate lists (64 x k=100, then 32 x k=1000)",
+        "match_labels_kernel": "32 x 1000 ids vs 2 gold ids", "sample_kernel": "labeled priority sampling, 32 x 1000 -> 8", "gather_picks_kernel": "take_along_axis + max_sampling_id",
+        "merge_kernel": "8 shards x 64 queries x 100 -> 100", "merge_results_kernel": "hybrid merge, 32 rows, 4 + 1000 + 1000 entries"}
+seen = {}
+for rr in rows[2:]:
+    nm = rr[ix['Kernel Name']].split('unnamed>::', 1)[-1].split('(')[0]; base = nm.split('<')[0]
+    key = (base, rr[ix['Grid Size']])
+    if key in seen: continue
+    seen[key] = 1
+    g = lambda k: float(rr[ix[k]])
+    A(f"| `{nm}` | {rr[ix['Grid Size']]} x {rr[ix['Block Size']]} | {g('gpu__time_duration.sum')*1e3:.1f} | {g('dram__bytes_read.sum')*1e3:.2f} | {int(g('launch__registers_per_thread'))} | {g('sm__warps_active.avg.pct_of_peak_sustained_active'):.0f} | {g('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'):.0f} | {what.get(base, '')} |")
+A("\nThe fp32-exact CUDA-core scan runs the big segment at 34 TFLOP/s (FMA pipe 49% active, 25% occupancy at 105 registers): compute-bound at 13% of HBM bandwidth, which is why a bf16/fp16 store with 3-term queries on the tensor cores (`tensor3`, same 1e-5 parity) is the recommended exact mode. Everything else is a latency-bound single wave (6-45 us).\n")
 A("## Epilogue history (8192-query batch, segment with ~19 survivors per 128x256 item)\n")
 A("| version | that segment | whole batch |\n|---|---|---|")
 A("| r01a: warp-aggregated global atomic per surviving column, L2 round trip inside the epilogue | 93 ms, 20% of the MMA rate | 190.5 ms, 39.7% of peak |")
