@@ -238,8 +238,6 @@ def test_error_paths():
     with pytest.raises(vod_b200.VodbError):
         st.search(np.zeros((1, 8), np.float32), 4096)
     with pytest.raises(vod_b200.VodbError):
-        st.search(np.zeros((1, 8), np.float32), 3, mode="tensor")  # fp32 store has no tensor path
-    with pytest.raises(vod_b200.VodbError):
         st.add(np.ones((5, 8), np.float32), row0=8)
     s, i = st.search(np.zeros((0, 8), np.float32), 3)
     assert s.shape == (0, 3)
@@ -290,6 +288,78 @@ def test_multi_term_modes_bit_exact_on_integer_data(mode):
     rs, ri = flat_ip.search(xb, xq, 64)
     assert np.array_equal(i, ri) and np.array_equal(s, rs)
     st.close()
+
+
+def test_fp32_store_on_tensor_cores_meets_the_fp32_exact_tolerance():
+    """A float32 store searched on the tensor cores: the rows are kept as three bf16 planes (row = p0 + p1 + p2
+    exactly), the float32 queries as three bf16 terms, and the six products c_p * q_t with p + t <= 2 accumulate in
+    fp32 — IndexFlatIP parity at the fp32-exact tolerance on arbitrary float32 data (BASELINE config 1 shape), also
+    after rows are appended or overwritten (the planes follow the store)."""
+    rng = np.random.default_rng(1234)
+    xb = rng.standard_normal((100_000, 768), dtype=np.float32)
+    xq = rng.standard_normal((256, 768), dtype=np.float32)
+    st = vod_b200.CorpusStore(len(xb), 768, dtype="float32")
+    st.add(xb[:60_000])
+    s, i = st.search(xq[:64], 100, mode="tensor3")          # planes built for the first 60k rows
+    rs, ri = flat_ip.search(xb[:60_000], xq[:64], 100)
+    rep = flat_ip.compare_topk(xb[:60_000], xq[:64], s, i, rs, ri, rtol=RTOL)
+    assert rep["ok"], rep
+    st.add(xb[60_000:], row0=60_000)                        # planes extended
+    rs, ri = flat_ip.search(xb, xq, 100)
+    recalls = {}
+    for mode in ("tensor", "tensor2", "tensor3"):
+        s, i = st.search(xq, 100, mode=mode)
+        recalls[mode] = flat_ip.recall_at_k(i, ri)
+        assert (np.diff(s, axis=1) <= 0).all()
+        if mode == "tensor3":
+            rep = flat_ip.compare_topk(xb, xq, s, i, rs, ri, rtol=RTOL)
+            assert rep["ok"], rep
+            # leading product and corrections are accumulated apart (the tensor core truncates every accumulation):
+            # the scores sit well inside the tolerance, not at its edge
+            assert rep["max_score_rel_err"] <= 4e-6, rep
+    assert recalls["tensor3"] >= 0.9995 and recalls["tensor2"] >= 0.999 and recalls["tensor"] >= 0.9, recalls
+    se, ie = st.search(xq, 100, mode="exact")               # the CUDA-core kernel agrees on the same store
+    assert flat_ip.recall_at_k(ie, i) >= 0.9995
+    xb[:1000] = rng.standard_normal((1000, 768), dtype=np.float32) * 3   # overwrite rows: planes redone from row 0
+    st.add(xb[:1000], row0=0)
+    s, i = st.search(xq[:9], 100, mode="tensor3")
+    rs, ri = flat_ip.search(xb, xq[:9], 100)
+    rep = flat_ip.compare_topk(xb, xq[:9], s, i, rs, ri, rtol=RTOL)
+    assert rep["ok"], rep
+    assert np.isin(i, np.arange(1000)).mean() > 0.5         # the rescaled rows now dominate the top-100
+    st.close()
+
+
+@pytest.mark.parametrize("mode", ["tensor", "tensor2", "tensor3"])
+@pytest.mark.parametrize("n,d,nq,k", [(5, 100, 3, 8), (1000, 130, 65, 7), (40_000, 96, 257, 100)])
+def test_fp32_store_tensor_modes_bit_exact_on_integer_data(mode, n, d, nq, k):
+    rng = np.random.default_rng(n + nq)
+    xb, xq = int_valued(rng, (n, d)), int_valued(rng, (nq, d))
+    st = _store(xb, "float32")
+    s, i = st.search(xq, k, mode=mode)
+    rs, ri = flat_ip.search(xb, xq, k)
+    assert np.array_equal(i, ri) and np.array_equal(s, rs)
+    st.close()
+
+
+def test_stale_query_staging_rows_never_reach_the_filter():
+    """Regression: a 9-query tensor-mode search right after a 64-query exact-mode search. The staging rows 9..63
+    still hold the float32 bit patterns of the earlier batch, which read as bf16 include inf / NaN; they must be
+    cleared, or unused accumulator columns produce +inf scores that pass the threshold filter."""
+    rng = np.random.default_rng(5)
+    xb = rng.standard_normal((50_000, 256), dtype=np.float32)
+    xb[:500] *= 3                                            # strong rows first: tight thresholds early
+    xq = rng.standard_normal((64, 256), dtype=np.float32)
+    for dtype in ("bfloat16", "float32"):
+        st = _store(round_to(xb, dtype) if dtype != "float32" else xb, dtype)
+        ref = round_to(xb, dtype) if dtype != "float32" else xb
+        st.search(xq * 1e30, 10, mode="exact")               # leaves huge float32 values in the staging buffer
+        s, i = st.search(xq[:9], 100, mode="tensor3")
+        rs, ri = flat_ip.search(ref, xq[:9], 100)
+        rep = flat_ip.compare_topk(ref, xq[:9], s, i, rs, ri, rtol=RTOL)
+        assert rep["ok"], rep
+        assert st.stats()["safe_fallback"] == 0
+        st.close()
 
 
 def _remote_worker(blob, q):

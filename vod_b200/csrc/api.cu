@@ -104,8 +104,8 @@ __global__ void convert_rows_kernel(const S* __restrict__ src, int src_dim, D* _
 // 3 bf16 / 2-3 fp16 terms reproduce the float32 query exactly (barring fp16 range limits).
 template <typename S, typename D>
 __global__ void prepare_kernel(const S* __restrict__ src, int src_dim, D* __restrict__ dst, int dst_pitch, int64_t n,
-                               int64_t plane_rows, int terms, int* __restrict__ cnt, float* __restrict__ tau,
-                               int first_rows) {
+                               int64_t plane_rows, int64_t fill_rows, int terms, int* __restrict__ cnt,
+                               float* __restrict__ tau, int first_rows) {
   pdl_launch_dependents();
   pdl_wait();  // the previous search on this stream may still be reading the staging buffer / lists
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,15 +113,35 @@ __global__ void prepare_kernel(const S* __restrict__ src, int src_dim, D* __rest
     cnt[gtid] = first_rows;
     tau[gtid] = -INFINITY;
   }
-  int64_t total = n * dst_pitch;
+  // rows [n, fill_rows) are the rest of the last query tile: zero them, so that whatever an earlier call left there
+  // (possibly inf / NaN bit patterns of another dtype) never reaches the MMAs — a garbage +inf score would pass the
+  // `score >= tau` filter of an unused column even against tau = +inf
+  int64_t total = fill_rows * dst_pitch;
   for (int64_t e = gtid; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = e / dst_pitch;
     int c = (int)(e - r * dst_pitch);
-    float v = (c < src_dim) ? to_f32<S>(src[r * src_dim + c]) : 0.0f;
+    float v = (r < n && c < src_dim) ? to_f32<S>(src[r * src_dim + c]) : 0.0f;
     for (int t = 0; t < terms; ++t) {
       D d = from_f32<D>(v);
       dst[(size_t)t * plane_rows * dst_pitch + e] = d;
       v = __fsub_rn(v, to_f32<D>(d));
+    }
+  }
+}
+
+// fp32 store -> 3 bf16 planes with row = p0 + p1 + p2 exactly: p_i = bf16_rn(what p_0..p_{i-1} left), the remainders
+// are exact in float32 and the last one (<= 8 significant bits) is itself a bf16
+__global__ void split_planes_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t row0, int64_t n,
+                                    int pitch, int64_t plane_elems) {
+  const int64_t total = n * pitch;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t at = row0 * pitch + e;
+    float v = src[at];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const __nv_bfloat16 d = from_f32<__nv_bfloat16>(v);
+      dst[(size_t)t * plane_elems + at] = d;
+      v = __fsub_rn(v, to_f32<__nv_bfloat16>(d));
     }
   }
 }
@@ -223,15 +243,17 @@ namespace {
 template <typename S>
 int prepare_dispatch_dst(const void* src, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
                          int64_t plane_rows, int terms, int* cnt, float* tau, int first_rows, cudaStream_t st) {
-  int64_t total = n * dst_pitch;
-  if (total == 0) return VODB_OK;
+  // query tiles are 64, 128 or 256 rows (score_tc.cu launch_score_tensor): clear the rest of the last one
+  const int64_t fill_rows = std::min<int64_t>(plane_rows, n <= 64 ? 64 : n <= 128 ? 128 : (n + 255) / 256 * 256);
+  int64_t total = fill_rows * dst_pitch;
+  if (n == 0) return VODB_OK;
   int g = std::max(grid_for(total), (int)((n + 255) / 256));  // every query needs a thread for the list reset
   const S* s = reinterpret_cast<const S*>(src);
   cudaError_t e;
   switch (dst_dtype) {
-    case VODB_F32: e = launch_pdl(prepare_kernel<S, float>, dim3(g), dim3(256), 0, st, s, src_dim, (float*)dst, dst_pitch, n, plane_rows, 1, cnt, tau, first_rows); break;
-    case VODB_BF16: e = launch_pdl(prepare_kernel<S, __nv_bfloat16>, dim3(g), dim3(256), 0, st, s, src_dim, (__nv_bfloat16*)dst, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows); break;
-    case VODB_F16: e = launch_pdl(prepare_kernel<S, __half>, dim3(g), dim3(256), 0, st, s, src_dim, (__half*)dst, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows); break;
+    case VODB_F32: e = launch_pdl(prepare_kernel<S, float>, dim3(g), dim3(256), 0, st, s, src_dim, (float*)dst, dst_pitch, n, plane_rows, fill_rows, 1, cnt, tau, first_rows); break;
+    case VODB_BF16: e = launch_pdl(prepare_kernel<S, __nv_bfloat16>, dim3(g), dim3(256), 0, st, s, src_dim, (__nv_bfloat16*)dst, dst_pitch, n, plane_rows, fill_rows, terms, cnt, tau, first_rows); break;
+    case VODB_F16: e = launch_pdl(prepare_kernel<S, __half>, dim3(g), dim3(256), 0, st, s, src_dim, (__half*)dst, dst_pitch, n, plane_rows, fill_rows, terms, cnt, tau, first_rows); break;
     default: set_error("launch_prepare: bad destination dtype %d", dst_dtype); return VODB_EINVAL;
   }
   VODB_CUDA_CHECK(e);
@@ -248,6 +270,15 @@ int launch_prepare(const void* src, int src_dtype, int src_dim, void* dst, int d
   }
   set_error("bad src dtype %d", src_dtype);
   return VODB_EINVAL;
+}
+
+int launch_split_planes(const float* src, void* planes, int64_t row0, int64_t n, int pitch, int64_t n_rows,
+                        cudaStream_t st) {
+  if (n <= 0) return VODB_OK;
+  split_planes_kernel<<<grid_for(n * pitch), 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(planes), row0, n, pitch,
+                                                            n_rows * pitch);
+  VODB_CUDA_CHECK(cudaGetLastError());
+  return VODB_OK;
 }
 
 int launch_fill_synthetic(void* dst, int dtype, int dim, int pitch, uint64_t seed, int64_t global_row0, int64_t n,
@@ -413,6 +444,31 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
   return b;
 }
 
+// fp32 stores reach the tensor cores through three bf16 planes (6 more bytes per element, allocated on the first
+// tensor-mode search and extended after later adds). The 16-bit stores need nothing.
+int ensure_planes(vodb_store* s, cudaStream_t st) {
+  if (s->dtype != VODB_F32) return VODB_OK;
+  if (!s->planes) {
+    cudaError_t e = cudaMalloc(&s->planes, (size_t)3 * s->n_rows * s->pitch * sizeof(__nv_bfloat16));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      s->planes = nullptr;
+      set_error("tensor modes on a float32 store need %.1f GB for the bf16 planes (%s); use VODB_MODE_EXACT or a bf16 store",
+                3.0 * s->n_rows * s->pitch * 2 / 1e9, cudaGetErrorString(e));
+      return VODB_ENOMEM;
+    }
+    s->planes_rows_done = 0;
+    s->tmap_planes_valid = false;
+  }
+  if (s->planes_rows_done < s->n_added) {
+    int rc = launch_split_planes(reinterpret_cast<const float*>(s->data), s->planes, s->planes_rows_done,
+                                 s->n_added - s->planes_rows_done, s->pitch, s->n_rows, st);
+    if (rc != VODB_OK) return rc;
+    s->planes_rows_done = s->n_added;
+  }
+  return VODB_OK;
+}
+
 int run_scan(vodb_store* s, const void* q_dev, int q_dtype, int nq, int k, int mode, bool safe, float* out_s,
              int64_t* out_i, cudaStream_t st, const ExchangeDst* xd = nullptr) {
   Workspace& w = s->ws;
@@ -422,14 +478,18 @@ int run_scan(vodb_store* s, const void* q_dev, int q_dtype, int nq, int k, int m
   // lists; the first segment (dump mode) stores every score, so cnt starts at its row count
   const int64_t rows_pad = ((int64_t)nq + 255) / 256 * 256;
   const bool tensor = is_tensor_mode(mode);
-  int rc = launch_prepare(q_dev, q_dtype, s->dim, w.q_stage, tensor ? s->dtype : VODB_F32, s->pitch, nq, rows_pad,
-                          tensor ? mode_terms(mode) : 1, w.cnt, w.tau, (int)(b[1] - b[0]), st);
+  const bool planes = tensor && s->dtype == VODB_F32;   // fp32 store: bf16 planes x bf16 query terms
+  const int tc_dtype = planes ? VODB_BF16 : s->dtype;   // what the tensor-core kernel multiplies
+  int rc = planes ? ensure_planes(s, st) : VODB_OK;
+  if (rc != VODB_OK) return rc;
+  rc = launch_prepare(q_dev, q_dtype, s->dim, w.q_stage, tensor ? tc_dtype : VODB_F32, s->pitch, nq, rows_pad,
+                      tensor ? mode_terms(mode) : 1, w.cnt, w.tau, (int)(b[1] - b[0]), st);
   if (rc != VODB_OK) return rc;
   int64_t launches = 1;
   for (size_t i = 0; i + 1 < b.size(); ++i) {
     SegmentArgs a;
-    a.corpus = s->data;
-    a.dtype = s->dtype;
+    a.corpus = planes ? s->planes : s->data;
+    a.dtype = tensor ? tc_dtype : s->dtype;
     a.pitch = s->pitch;
     a.row_begin = b[i];
     a.row_end = b[i + 1];
@@ -442,7 +502,8 @@ int run_scan(vodb_store* s, const void* q_dev, int q_dtype, int nq, int k, int m
     a.overflow = w.overflow;
     a.cap = w.cap;
     a.dump = (i == 0);
-    a.terms = is_tensor_mode(mode) ? mode_terms(mode) : 1;
+    a.terms = tensor ? mode_terms(mode) : 1;
+    a.planes = planes ? a.terms : 1;
     ProfileState* prof = s->profiling ? static_cast<ProfileState*>(s->prof) : nullptr;
     if (prof) cudaEventRecord(prof->next(), st);
     rc = is_tensor_mode(mode) ? launch_score_tensor(s, a, st) : launch_score_exact(a, s->sm_count, st);
@@ -585,6 +646,7 @@ void vodb_store_destroy(vodb_store* s) {
     delete p;
   }
   if (s->stage) cudaFree(s->stage);
+  if (s->planes) cudaFree(s->planes);
   if (s->data) cudaFree(s->data);
   delete s;
 }
@@ -625,6 +687,7 @@ int vodb_store_add(vodb_store* s, const void* rows, int src_dtype, int src_on_de
     }
   }
   s->n_added = std::max(s->n_added, row0 + n);
+  s->planes_rows_done = std::min(s->planes_rows_done, row0);  // bf16 planes of an fp32 store: redo from here
   return VODB_OK;
 }
 
@@ -637,6 +700,7 @@ int vodb_store_fill_synthetic(vodb_store* s, uint64_t seed, int64_t row0, int64_
                                  reinterpret_cast<cudaStream_t>(stream));
   if (rc != VODB_OK) return rc;
   s->n_added = std::max(s->n_added, row0 + n);
+  s->planes_rows_done = std::min(s->planes_rows_done, row0);
   return VODB_OK;
 }
 
@@ -681,7 +745,7 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
     return VODB_ESTATE;
   }
   if (is_tensor_mode(mode) && !tensor_path_supported(s)) {
-    set_error("vodb_search: VODB_MODE_TENSOR* needs a bf16/f16 store and a driver exporting cuTensorMapEncodeTiled");
+    set_error("vodb_search: VODB_MODE_TENSOR* needs a driver exporting cuTensorMapEncodeTiled");
     return VODB_EUNSUPPORTED;
   }
   DeviceGuard guard(s->device);
@@ -1076,7 +1140,7 @@ int vodb_retrieve_sample(vodb_store* s, const void* queries, int q_dtype, int q_
     return VODB_ESTATE;
   }
   if (is_tensor_mode(mode) && !tensor_path_supported(s)) {
-    set_error("vodb_retrieve_sample: VODB_MODE_TENSOR* needs a bf16/f16 store and a driver exporting cuTensorMapEncodeTiled");
+    set_error("vodb_retrieve_sample: VODB_MODE_TENSOR* needs a driver exporting cuTensorMapEncodeTiled");
     return VODB_EUNSUPPORTED;
   }
   DeviceGuard guard(s->device);

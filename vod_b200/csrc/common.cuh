@@ -146,6 +146,12 @@ struct vodb_store {
   // TMA descriptor cache for the tensor-core path (opaque CUtensorMap storage)
   alignas(64) unsigned char tmap_corpus[128];
   bool tmap_corpus_valid = false;
+  // fp32 stores on the tensor cores: bf16 planes [3][n_rows][pitch] with data = p0 + p1 + p2 exactly, built on the
+  // first tensor-mode search (6 more bytes per element) and extended after later adds
+  void* planes = nullptr;
+  int64_t planes_rows_done = 0;  // rows [0, planes_rows_done) of the planes are up to date
+  alignas(64) unsigned char tmap_planes[128];
+  bool tmap_planes_valid = false;
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // optional per-kernel timing (vodb_store_set_profiling): events recorded around every scan launch
   bool profiling = false;
@@ -156,8 +162,8 @@ namespace vodb {
 
 // ---- kernels launched by the search pipeline (defined in the .cu files) ----------
 struct SegmentArgs {
-  const void* corpus;   // [n_rows, pitch]
-  int dtype;
+  const void* corpus;   // [n_rows, pitch]; fp32 store in tensor mode: bf16 planes [3][n_rows][pitch]
+  int dtype;            // dtype of what the scoring kernel reads (store dtype, or bf16 for the planes)
   int pitch;
   int64_t row_begin;    // segment [row_begin, row_end) of local rows
   int64_t row_end;
@@ -170,6 +176,7 @@ struct SegmentArgs {
   int* overflow;
   int cap;
   int terms;            // TENSOR: 16-bit terms per query (1..3), staged as [terms][round_up(nq,256)][pitch]
+  int planes;           // TENSOR on an fp32 store: bf16 corpus planes used (= terms); 1 otherwise
   bool dump;            // first segment of a scan: lists are empty, every score is stored at slot row-row_begin
 };
 
@@ -207,6 +214,8 @@ int launch_convert_rows(const void* src, int src_dtype, int src_dim, void* dst, 
 // candidate lists (cnt = rows of the first segment, tau = -inf) in one launch
 int launch_prepare(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
                    int64_t plane_rows, int terms, int* cnt, float* tau, int first_rows, cudaStream_t stream);
+int launch_split_planes(const float* src, void* planes, int64_t row0, int64_t n, int pitch, int64_t n_rows,
+                        cudaStream_t stream);
 int launch_fill_synthetic(void* dst, int dtype, int dim, int pitch, uint64_t seed, int64_t global_row0, int64_t n,
                           int unit_norm, cudaStream_t stream);
 int launch_read_rows(const void* src, int dtype, int dim, int pitch, int64_t n, float* out, cudaStream_t stream);

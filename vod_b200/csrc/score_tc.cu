@@ -138,6 +138,7 @@ struct TcParams {
   int n_ctiles, n_qtiles;
   int kchunks;  // pitch / KC
   int q_rows_pad;  // rows of one query term plane in the staged query tensor [terms][q_rows_pad][pitch]
+  int plane_rows;  // rows of one corpus plane in the corpus tensor map (fp32 stores searched through bf16 planes)
   float* cand_s;
   int32_t* cand_i;
   int* cnt;
@@ -249,14 +250,23 @@ __device__ __forceinline__ void epilogue_begin_item(const TcParams& p, WarpStage
 
 // the BN score columns of this thread's corpus row: dump them (first segment) or filter against tau and push the
 // rare survivors into the warp's staging buffer
-template <int BN>
+// DUAL: the score is the sum of two accumulators, columns [0, BN) (leading product) and [BN, 2 BN) (corrections)
+template <int BN, bool DUAL = false>
 __device__ __forceinline__ void epilogue_columns(const TcParams& p, WarpStage& ws, const float* tau_cur,
                                                  uint32_t taddr0, int64_t row, bool valid, int q0, int sb) {
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     uint32_t v[32];
     tmem_ld_32x32b_x32(taddr0 + (uint32_t)c0, v);
-    tmem_ld_wait();
+    if constexpr (DUAL) {
+      uint32_t w[32];
+      tmem_ld_32x32b_x32(taddr0 + (uint32_t)(BN + c0), w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(w[j])));
+    } else {
+      tmem_ld_wait();
+    }
     if (p.dump) {
       // first segment: every score is a candidate; slot = row - row_begin, no atomics, coalesced over lanes
       if (valid) {
@@ -311,26 +321,39 @@ __device__ __forceinline__ void epilogue_columns(const TcParams& p, WarpStage& w
   }
 }
 
-// BN = queries per tile (MMA N); T = query terms: a float32 query is split into T 16-bit terms (hi, lo, lo2) whose
-// partial products accumulate into the same TMEM accumulator, so T=2 keeps ~16 and T=3 all 24 mantissa bits of
-// the query while the corpus tile is loaded from HBM/L2 only once per stage.
-template <int BN, int T>
+// BN = queries per tile (MMA N); T = query terms: a float32 query is split into T 16-bit terms (hi, lo, lo2), so T=2
+// keeps ~16 and T=3 all 24 mantissa bits of the query while the corpus tile is loaded from HBM/L2 only once per
+// stage. With T > 1 an item has TWO accumulators: the leading product (hi x hi) and the sum of the correction
+// products, added once in the epilogue. The tensor core truncates (does not round) every accumulation, a bias of up
+// to one ulp of the accumulator per MMA; keeping the small corrections apart leaves kchunks*4 truncations at full
+// magnitude instead of kchunks*4*T (or *6 with corpus planes): 1.5e-6 instead of 1e-5 relative at dim 768.
+//
+// P > 1 (fp32 store, api.cu `ensure_planes`): the corpus is held as P bf16 planes c = c_0 + c_1 + c_2 (each the bf16
+// rounding of what the previous ones left, so 3 planes carry all 24 mantissa bits) and the queries as T = P terms; the
+// kernel accumulates the products c_p * q_t with p + t < P (6 of 9 for P = 3: the dropped ones are below 2^-24 of
+// the leading product), every one exact in the fp32 accumulator. A pipeline stage is one (K chunk, plane) pair:
+// the plane's corpus box plus the P - p query boxes it is multiplied with.
+template <int BN, int T, int P = 1>
 struct TcConfig {
+  static_assert(P == 1 || P == T, "corpus planes come with as many query terms");
   static constexpr uint32_t kABytes = BM * KC * 2;
   static constexpr uint32_t kBBytes = BN * KC * 2;          // one term
   static constexpr uint32_t kStageBytes = kABytes + T * kBBytes;
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
-  static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                        : (2 * BN <= 256) ? 256 : 512;
+  static constexpr bool kDual = (T > 1);
+  static constexpr uint32_t kAccCols = (kDual ? 2 : 1) * BN;  // TMEM columns of one accumulator buffer
+  static_assert(2 * kAccCols <= 512, "two accumulator buffers must fit the 512 TMEM columns");
+  static constexpr uint32_t kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
+                                        : (2 * kAccCols <= 256) ? 256 : 512;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
                                          4 * BN * sizeof(float) /*tau, one copy per epilogue warp*/ + 4 * sizeof(WarpStage);
 };
 
-template <int BN, int T>
+template <int BN, int T, int P = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_constant__ CUtensorMap tmap_query,
                 const TcParams p) {
-  using Cfg = TcConfig<BN, T>;
+  using Cfg = TcConfig<BN, T, P>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle (TMA writes and UMMA reads XOR address bits [4,7) with [7,10))
@@ -391,14 +414,19 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
         const int row0 = (int)(p.row_begin + (int64_t)ct * BM);
         const int q0 = qt * BN;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC, row0, corpus_policy);
 #pragma unroll
-          for (int t = 0; t < T; ++t)
-            tma_load_2d(&tmap_query, &full_bar[stage], smem_b + (stage * T + t) * Cfg::kBBytes, kc * KC,
-                        t * p.q_rows_pad + q0, kEvictLast);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          for (int pl = 0; pl < P; ++pl) {
+            const int nt = (P == 1) ? T : (P - pl);  // query terms multiplied with this plane
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::kABytes + (uint32_t)nt * Cfg::kBBytes);
+            tma_load_2d(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC,
+                        pl * p.plane_rows + row0, corpus_policy);
+#pragma unroll
+            for (int t = 0; t < nt; ++t)
+              tma_load_2d(&tmap_query, &full_bar[stage], smem_b + (stage * T + t) * Cfg::kBBytes, kc * KC,
+                          t * p.q_rows_pad + q0, kEvictLast);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -413,22 +441,29 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * Cfg::kAccCols;  // leading product; corrections at + BN
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
-          tcgen05_fence_after();
-          const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
 #pragma unroll
-          for (int t = 0; t < T; ++t) {
-            const uint64_t db = make_desc_sw128(smem_u32(smem_b + (stage * T + t) * Cfg::kBBytes));
+          for (int pl = 0; pl < P; ++pl) {
+            const int nt = (P == 1) ? T : (P - pl);
+            mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
+            tcgen05_fence_after();
+            const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
 #pragma unroll
-            for (int k = 0; k < KC / UMMA_K; ++k) {
-              // advance 32 bytes (16 elements) inside the 128-byte swizzle atom: +2 in the >>4 address field
-              umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kc | t | k) != 0 ? 1u : 0u);
+            for (int t = 0; t < nt; ++t) {
+              const uint64_t db = make_desc_sw128(smem_u32(smem_b + (stage * T + t) * Cfg::kBBytes));
+#pragma unroll
+              for (int k = 0; k < KC / UMMA_K; ++k) {
+                // advance 32 bytes (16 elements) inside the 128-byte swizzle atom: +2 in the >>4 address field
+                const bool lead = (pl == 0 && t == 0);
+                const bool first = (kc | k) == 0 && (lead || (pl == 0 && t == 1));  // first MMA into its accumulator
+                umma_f16(lead ? tmem_d : tmem_d + (uint32_t)BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
+                         first ? 0u : 1u);
+              }
             }
+            umma_commit(&empty_bar[stage]);  // frees the smem stage once the MMAs above have read it
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage once the MMAs above have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
       }
@@ -456,8 +491,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_columns<BN>(p, ws, tau_cur, taddr0, row, valid, q0, sb);
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * Cfg::kAccCols;
+      epilogue_columns<BN, Cfg::kDual>(p, ws, tau_cur, taddr0, row, valid, q0, sb);
       // all TMEM reads of this buffer are complete (wait::ld above): hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
@@ -741,20 +776,34 @@ int encode_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int p
   return VODB_OK;
 }
 
-template <int BN, int T>
-int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
-  using Cfg = TcConfig<BN, T>;
-  static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
-  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&score_tc_kernel<BN, T>), Cfg::kSmemBytes));
-  if (!s->tmap_corpus_valid) {
-    int rc = encode_2d(reinterpret_cast<CUtensorMap*>(s->tmap_corpus), s->data, s->dtype, s->n_rows, s->pitch, BM);
+// corpus tensor map (cached in the store): the rows themselves (bf16 / fp16 store), or the bf16 planes of an fp32
+// store stacked along the rows ([3 * n_rows, pitch]; plane p of row r is row p * n_rows + r)
+int corpus_tensor_map(vodb_store* s, const CUtensorMap** out) {
+  const bool planes = (s->dtype == VODB_F32);
+  unsigned char* storage = planes ? s->tmap_planes : s->tmap_corpus;
+  bool& valid = planes ? s->tmap_planes_valid : s->tmap_corpus_valid;
+  if (!valid) {
+    int rc = planes ? encode_2d(reinterpret_cast<CUtensorMap*>(storage), s->planes, VODB_BF16, 3 * s->n_rows, s->pitch, BM)
+                    : encode_2d(reinterpret_cast<CUtensorMap*>(storage), s->data, s->dtype, s->n_rows, s->pitch, BM);
     if (rc != VODB_OK) return rc;
-    s->tmap_corpus_valid = true;
+    valid = true;
   }
+  *out = reinterpret_cast<const CUtensorMap*>(storage);
+  return VODB_OK;
+}
+
+template <int BN, int T, int P = 1>
+int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
+  using Cfg = TcConfig<BN, T, P>;
+  static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
+  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&score_tc_kernel<BN, T, P>), Cfg::kSmemBytes));
+  const CUtensorMap* tmap_store = nullptr;
+  int rc = corpus_tensor_map(s, &tmap_store);
+  if (rc != VODB_OK) return rc;
   alignas(64) CUtensorMap tmap_q;
   // the staged query buffer is zero padded to a multiple of 256 rows (api.cu), so every BN-row box is in bounds
   const int64_t q_rows_pad = ((int64_t)a.nq + 255) / 256 * 256;
-  int rc = encode_2d(&tmap_q, a.queries, s->dtype, q_rows_pad * T, s->pitch, BN);
+  rc = encode_2d(&tmap_q, a.queries, a.dtype, q_rows_pad * T, s->pitch, BN);
   if (rc != VODB_OK) return rc;
 
   TcParams p;
@@ -765,6 +814,7 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.n_qtiles = (a.nq + BN - 1) / BN;
   p.kchunks = s->pitch / KC;
   p.q_rows_pad = (int)q_rows_pad;
+  p.plane_rows = (int)s->n_rows;
   p.cand_s = a.cand_s;
   p.cand_i = a.cand_i;
   p.cnt = a.cnt;
@@ -772,27 +822,25 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.overflow = a.overflow;
   p.cap = a.cap;
   p.dump = a.dump ? 1 : 0;
-  const uint32_t fmt = (s->dtype == VODB_BF16) ? 1u : 0u;  // UMMA F16F32Format: F16=0, BF16=1
+  const uint32_t fmt = (a.dtype == VODB_BF16) ? 1u : 0u;  // UMMA F16F32Format: F16=0, BF16=1
   p.idesc = (1u << 4) /*D=f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
   if (items <= 0) return VODB_OK;
   int grid = (int)(items < s->sm_count ? items : s->sm_count);
-  VODB_CUDA_CHECK(launch_pdl(score_tc_kernel<BN, T>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream,
-                             *reinterpret_cast<CUtensorMap*>(s->tmap_corpus), tmap_q, p));
+  VODB_CUDA_CHECK(launch_pdl(score_tc_kernel<BN, T, P>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream,
+                             *tmap_store, tmap_q, p));
   return VODB_OK;
 }
 
 int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   using Cfg = Tc2Config;
   VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&score_tc2_kernel), Cfg::kSmemBytes));
-  if (!s->tmap_corpus_valid) {
-    int rc0 = encode_2d(reinterpret_cast<CUtensorMap*>(s->tmap_corpus), s->data, s->dtype, s->n_rows, s->pitch, BM);
-    if (rc0 != VODB_OK) return rc0;
-    s->tmap_corpus_valid = true;
-  }
+  const CUtensorMap* tmap_store = nullptr;
+  int rc = corpus_tensor_map(s, &tmap_store);
+  if (rc != VODB_OK) return rc;
   alignas(64) CUtensorMap tmap_q;
   const int64_t q_rows_pad = ((int64_t)a.nq + 255) / 256 * 256;
-  int rc = encode_2d(&tmap_q, a.queries, s->dtype, q_rows_pad, s->pitch, Cfg::BN / 2);
+  rc = encode_2d(&tmap_q, a.queries, a.dtype, q_rows_pad, s->pitch, Cfg::BN / 2);
   if (rc != VODB_OK) return rc;
   TcParams p;
   p.row_begin = a.row_begin;
@@ -802,6 +850,7 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.n_qtiles = (a.nq + Cfg::BN - 1) / Cfg::BN;
   p.kchunks = s->pitch / KC;
   p.q_rows_pad = (int)q_rows_pad;
+  p.plane_rows = 0;
   p.cand_s = a.cand_s;
   p.cand_i = a.cand_i;
   p.cnt = a.cnt;
@@ -809,7 +858,7 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.overflow = a.overflow;
   p.cap = a.cap;
   p.dump = a.dump ? 1 : 0;
-  const uint32_t fmt = (s->dtype == VODB_BF16) ? 1u : 0u;
+  const uint32_t fmt = (a.dtype == VODB_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cfg::BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
   if (items <= 0) return VODB_OK;
@@ -828,7 +877,7 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  VODB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, score_tc2_kernel, *reinterpret_cast<CUtensorMap*>(s->tmap_corpus), tmap_q, p));
+  VODB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, score_tc2_kernel, *tmap_store, tmap_q, p));
   return VODB_OK;
 }
 
@@ -836,13 +885,14 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
 bool use_pair_kernel(const SegmentArgs& a) {
   static const char* env = std::getenv("VODB_TC2");
   const bool enabled = env ? (env[0] != '0') : true;
-  return enabled && a.terms == 1 && a.nq > 128;
+  return enabled && a.terms == 1 && a.planes == 1 && a.nq > 128;
 }
 
 }  // namespace
 
 bool tensor_path_supported(const vodb_store* s) {
-  return (s->dtype == VODB_BF16 || s->dtype == VODB_F16) && get_encode_fn() != nullptr;
+  // bf16 / fp16 stores natively; fp32 stores through their bf16 planes (api.cu ensure_planes)
+  return get_encode_fn() != nullptr;
 }
 
 int launch_score_tensor(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
@@ -850,9 +900,17 @@ int launch_score_tensor(vodb_store* s, const SegmentArgs& a, cudaStream_t stream
     set_error("launch_score_tensor: segment start %lld is not a multiple of %d", (long long)a.row_begin, BM);
     return VODB_EINVAL;
   }
-  if ((int64_t)s->n_rows > 0x7fffffffLL) {
+  if ((int64_t)s->n_rows * (a.planes > 1 ? 3 : 1) > 0x7fffffffLL) {
     set_error("launch_score_tensor: shard too large for 32-bit TMA coordinates");
     return VODB_EUNSUPPORTED;
+  }
+  if (a.planes > 1) {  // fp32 store: P bf16 corpus planes x P query terms
+    if (a.planes != a.terms) {
+      set_error("launch_score_tensor: %d corpus planes need as many query terms (got %d)", a.planes, a.terms);
+      return VODB_EINVAL;
+    }
+    if (a.planes == 2) return a.nq <= 64 ? launch_bn<64, 2, 2>(s, a, stream) : launch_bn<128, 2, 2>(s, a, stream);
+    return a.nq <= 64 ? launch_bn<64, 3, 3>(s, a, stream) : launch_bn<128, 3, 3>(s, a, stream);
   }
   if (use_pair_kernel(a)) return launch_pair(s, a, stream);
   switch (a.terms) {
