@@ -95,6 +95,13 @@ for rr in rows[2:]:
     g = lambda k: float(rr[ix[k]])
     A(f"| `{nm}` | {rr[ix['Grid Size']]} x {rr[ix['Block Size']]} | {g('gpu__time_duration.sum')*1e3:.1f} | {g('dram__bytes_read.sum')*1e3:.2f} | {int(g('launch__registers_per_thread'))} | {g('sm__warps_active.avg.pct_of_peak_sustained_active'):.0f} | {g('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'):.0f} | {what.get(base, '')} |")
 A("\nThe fp32-exact CUDA-core scan runs the big segment at 34 TFLOP/s (FMA pipe 49% active, 25% occupancy at 105 registers): compute-bound at 13% of HBM bandwidth, which is why a bf16/fp16 store with 3-term queries on the tensor cores (`tensor3`, same 1e-5 parity) is the recommended exact mode. Everything else is a latency-bound single wave (6-45 us).\n")
+fp = json.loads((P / 'r01k_fp32_planes_probe.json').read_text())
+A("## float32 store: CUDA-core exact kernel vs tensor cores over bf16 planes (r01k_fp32_planes_probe.json, scripts/probe_fp32_planes.py; 4M x 768 fp32 = 12.3 GB, top-100)\n")
+A("| queries | exact (CUDA cores) ms | tensor3 ms (speed-up; GB/s of fp32 bytes; recall vs exact) | tensor2 ms (recall) | tensor ms (recall) |\n|---|---|---|---|---|")
+for nq in (64, 256, 1024):
+    e = fp[f'q{nq}_exact_ms']; t3 = fp[f'q{nq}_tensor3_ms']
+    A(f"| {nq} | {e:.2f} | {t3:.2f} ({e/t3:.1f}x; {fp[f'q{nq}_tensor3_GBps_of_fp32_bytes']:.0f}; {fp[f'q{nq}_tensor3_recall_vs_exact']:.5f}) | {fp[f'q{nq}_tensor2_ms']:.2f} ({fp[f'q{nq}_tensor2_recall_vs_exact']:.5f}) | {fp[f'q{nq}_tensor_ms']:.2f} ({fp[f'q{nq}_tensor_recall_vs_exact']:.4f}) |")
+A("\ntensor3 reads 6 bytes per stored element (three bf16 planes) and issues 6 MMAs per K step; at 64 queries it runs at 80% of the HBM time of those 18.4 GB. Scores agree with a float64 re-score to <= 4e-6 relative (two accumulators per item: leading product / corrections).\n")
 A("## Epilogue history (8192-query batch, segment with ~19 survivors per 128x256 item)\n")
 A("| version | that segment | whole batch |\n|---|---|---|")
 A("| r01a: warp-aggregated global atomic per surviving column, L2 round trip inside the epilogue | 93 ms, 20% of the MMA rate | 190.5 ms, 39.7% of peak |")
