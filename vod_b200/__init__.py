@@ -13,6 +13,7 @@ from .sampling import (PrioritySampledSections, labeled_priority_sampling, prior
 from .search import (B200SearchClient, B200SearchMaster, CorpusStore, DoNotPickleError, SearchClient,
                      build_b200_index, merge_topk, merge_topk_device)
 from .hybrid import async_hybrid_search, merge_search_results, normalize_search_scores_
+from .collate import flatten_samples, gather_values_by_indices, replace_negative_indices_
 from .routing import ShardedSearchClient
 from .sharded import MultiGpuStore, ShardedCorpus, ShardedSearcher, shard_bounds
 
@@ -22,4 +23,5 @@ __all__ = [
     "ShardedSearcher", "async_hybrid_search", "merge_search_results", "normalize_search_scores_",
     "VodbError", "VodbUnavailableError", "build_b200_index", "labeled_priority_sampling", "merge_topk",
     "merge_topk_device", "priority_sampling_1d", "sample_search_results", "shard_bounds",
+    "flatten_samples", "gather_values_by_indices", "replace_negative_indices_",
 ]
