@@ -95,6 +95,12 @@ for rr in rows[2:]:
     g = lambda k: float(rr[ix[k]])
     A(f"| `{nm}` | {rr[ix['Grid Size']]} x {rr[ix['Block Size']]} | {g('gpu__time_duration.sum')*1e3:.1f} | {g('dram__bytes_read.sum')*1e3:.2f} | {int(g('launch__registers_per_thread'))} | {g('sm__warps_active.avg.pct_of_peak_sustained_active'):.0f} | {g('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'):.0f} | {what.get(base, '')} |")
 A("\nThe fp32-exact CUDA-core scan runs the big segment at 34 TFLOP/s (FMA pipe 49% active, 25% occupancy at 105 registers): compute-bound at 13% of HBM bandwidth, which is why a bf16/fp16 store with 3-term queries on the tensor cores (`tensor3`, same 1e-5 parity) is the recommended exact mode. Everything else is a latency-bound single wave (6-45 us).\n")
+sw = [json.loads(l) for l in (P / 'r01k_batch_sweep.jsonl').read_text().splitlines() if l.startswith('{')]
+A("## Roofline curve over the batch size (r01k_batch_sweep.jsonl, scripts/sweep_batch.py; 10M x 768 bf16, top-100, back-to-back searches)\n")
+A("| queries | ms | queries/s | roofline ms = max(bytes / HBM peak, flops / bf16 burst peak) | fraction | bound | segments |\n|---|---|---|---|---|---|---|")
+for r in sw:
+    A(f"| {r['nq']} | {r['ms']:.3f} | {r['qps']:.0f} | {r['roofline_ms']:.3f} | {r['frac']*100:.0f}% | {r['bound']} | {r['segments']} |")
+A("\nQuery tiles are 64 / 128 (1-CTA kernel) or 256 wide (CTA pair), so 257-511 queries cost what 512 cost; around the crossover (128-512 queries) HBM and tensor pipe are both near their limits and share one power budget, which is where the fraction of the max() roofline is lowest. Run-to-run spread on one box at 384-512 queries was +-15% (5.8-7.1 ms at 512) with the clocks under `sw_power_cap`.\n")
 fp = json.loads((P / 'r01k_fp32_planes_probe.json').read_text())
 A("## float32 store: CUDA-core exact kernel vs tensor cores over bf16 planes (r01k_fp32_planes_probe.json, scripts/probe_fp32_planes.py; 4M x 768 fp32 = 12.3 GB, top-100)\n")
 A("| queries | exact (CUDA cores) ms | tensor3 ms (speed-up; GB/s of fp32 bytes; recall vs exact) | tensor2 ms (recall) | tensor ms (recall) |\n|---|---|---|---|---|")
