@@ -409,11 +409,21 @@ def main():
                 b1.record()
                 torch.cuda.synchronize()
                 samp.append(b0.elapsed_time(b1) * 1e3)
+            # the reference-facing sampling call on host arrays (what RealmCollate calls after a hybrid merge)
+            rb = vod_b200.RetrievalBatch(scores=sc4.cpu().numpy(), indices=np.tile(np.arange(1000, dtype=np.int64), (32, 1)))
+            host_call = []
+            for i in range(30):
+                t0 = time.perf_counter()
+                vod_b200.sample_search_results(search_results=rb, raw_scores={"dense": rb.scores}, total=8,
+                                               max_pos_sections=3, seed=42, offset=i)
+                host_call.append((time.perf_counter() - t0) * 1e3)
+            host_call = sorted(host_call[5:])
             times, samp = sorted(times[5:]), sorted(samp[5:])
             config4 = {"workload": "32 queries -> exact top-1000 over the 10M x 768 bf16 shard -> labeled priority sampling of 8 "
                                    "(host queries in, [32,8] picks + log-weights out, one D2H)",
                        "chain_ms_p50": times[len(times) // 2], "chain_ms_p90": times[(len(times) * 9) // 10],
-                       "sampler_kernel_us_p50": samp[len(samp) // 2]}
+                       "sampler_kernel_us_p50": samp[len(samp) // 2],
+                       "sample_search_results_host_call_ms_p50": host_call[len(host_call) // 2]}
             config4["dataloader_workers"] = worker_clients_section(corpus.store)
         except Exception as exc:
             config4 = {"error": f"{type(exc).__name__}: {exc}"}

@@ -540,6 +540,39 @@ int run_scan(vodb_store* s, const void* q_dev, int q_dtype, int nq, int k, int m
 
 using namespace vodb;
 
+namespace {
+// Device scratch of the host-buffer entry points that have no store to hang a workspace on (vodb_sample,
+// vodb_merge_topk, vodb_merge_results): one grow-only buffer per device, held for the duration of a call, so that
+// a per-batch call costs copies + kernel instead of a cudaMalloc / cudaFree pair (the free alone synchronises the
+// device). Released at process exit with the context.
+struct CallScratch {
+  std::mutex mu;
+  char* dev = nullptr;
+  size_t bytes = 0;
+};
+CallScratch& call_scratch(int device) {
+  static CallScratch table[64];
+  return table[device >= 0 && device < 64 ? device : 0];
+}
+// returns nullptr (error set) when the allocation fails; the caller holds `cs.mu`
+char* scratch_reserve(CallScratch& cs, size_t bytes, const char* who) {
+  if (bytes > cs.bytes) {
+    if (cs.dev) cudaFree(cs.dev);
+    cs.dev = nullptr;
+    cs.bytes = 0;
+    const size_t want = bytes + bytes / 4;  // head-room: batch shapes repeat, widths wobble
+    cudaError_t e = cudaMalloc(&cs.dev, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("%s: cudaMalloc(%zu bytes) failed: %s", who, want, cudaGetErrorString(e));
+      return nullptr;
+    }
+    cs.bytes = want;
+  }
+  return cs.dev;
+}
+}  // namespace
+
 // Peer-mapped exchange buffer of one rank (vodb_xchg_*): [2 parities][world source ranks][slot entries][3 tagged
 // 8-byte words] (see ExchangeDst), zero-initialised, exported to the peers through CUDA IPC.
 struct vodb_xchg {
@@ -968,20 +1001,21 @@ int vodb_merge_topk(int device, const float* scores, const int64_t* idx, int n_l
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (on_device) return launch_merge(scores, idx, n_lists, nq, k_in, k_out, out_scores, out_idx, st);
   size_t n_in = (size_t)n_lists * nq * k_in, n_out = (size_t)nq * k_out;
-  float *d_s = nullptr, *d_os = nullptr;
-  int64_t *d_i = nullptr, *d_oi = nullptr;
+  CallScratch& cs = call_scratch(device);
+  std::lock_guard<std::mutex> lock(cs.mu);
+  char* d = scratch_reserve(cs, (n_in + n_out) * 12 + 64, "vodb_merge_topk");
+  if (!d) return VODB_ENOMEM;
+  int64_t* d_i = reinterpret_cast<int64_t*>(d);
+  int64_t* d_oi = d_i + n_in;
+  float* d_s = reinterpret_cast<float*>(d_oi + n_out);
+  float* d_os = d_s + n_in;
   int rc = VODB_OK;
-  cudaError_t e = cudaMalloc(&d_s, n_in * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&d_i, n_in * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&d_os, n_out * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&d_oi, n_out * 8);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, scores, n_in * 4, cudaMemcpyHostToDevice, st);
+  cudaError_t e = cudaMemcpyAsync(d_s, scores, n_in * 4, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_i, idx, n_in * 8, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) rc = launch_merge(d_s, d_i, n_lists, nq, k_in, k_out, d_os, d_oi, st);
   if (e == cudaSuccess && rc == VODB_OK) e = cudaMemcpyAsync(out_scores, d_os, n_out * 4, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess && rc == VODB_OK) e = cudaMemcpyAsync(out_idx, d_oi, n_out * 8, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d_s); cudaFree(d_i); cudaFree(d_os); cudaFree(d_oi);
   if (e != cudaSuccess) {
     set_error("vodb_merge_topk: %s", cudaGetErrorString(e));
     return VODB_ECUDA;
@@ -1025,8 +1059,10 @@ int vodb_merge_results(int device, int n_engines, const void* const* scores, con
   for (int e = 0; e < n_engines; ++e) in_bytes += (size_t)B * widths[e] * (fsz + 8 + 8);
   const size_t nout = (size_t)B * out_width;
   size_t out_bytes = nout * (fsz + 8 + 8) + (size_t)n_engines * nout * fsz + (size_t)B * 4 + 64;
-  char* d = nullptr;
-  VODB_CUDA_CHECK(cudaMalloc(&d, in_bytes + out_bytes + 256));
+  CallScratch& cs = call_scratch(device);
+  std::lock_guard<std::mutex> lock(cs.mu);
+  char* d = scratch_reserve(cs, in_bytes + out_bytes + 256, "vodb_merge_results");
+  if (!d) return VODB_ENOMEM;
   const void* d_scores[8];
   const int64_t* d_idx[8];
   const int64_t* d_lab[8];
@@ -1062,7 +1098,6 @@ int vodb_merge_results(int device, int n_engines, const void* const* scores, con
   if (e2 == cudaSuccess && rc == VODB_OK) e2 = cudaMemcpyAsync(out_raw, o_r, (size_t)n_engines * nout * fsz, cudaMemcpyDeviceToHost, st);
   if (e2 == cudaSuccess && rc == VODB_OK) e2 = cudaMemcpyAsync(out_counts, o_c, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
   if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
-  cudaFree(d);
   if (e2 != cudaSuccess) {
     set_error("vodb_merge_results: %s", cudaGetErrorString(e2));
     return VODB_ECUDA;
@@ -1093,8 +1128,10 @@ int vodb_sample(int device, const float* scores, const uint8_t* labels, const fl
   size_t off_scores = 0, off_noise = off_scores + nBK * 4, off_logw = off_noise + (noise ? nBK * 4 : 0);
   size_t off_lse = off_logw + nBk * 4, off_ids = (off_lse + (size_t)B * 8 + 7) / 8 * 8;
   size_t off_labels = off_ids + nBk * 8, off_olab = off_labels + (labels ? nBK : 0), total = off_olab + nBk + 16;
-  char* d = nullptr;
-  VODB_CUDA_CHECK(cudaMalloc(&d, total));
+  CallScratch& cs = call_scratch(device);
+  std::lock_guard<std::mutex> lock(cs.mu);
+  char* d = scratch_reserve(cs, total, "vodb_sample");
+  if (!d) return VODB_ENOMEM;
   int rc = VODB_OK;
   cudaError_t e = cudaMemcpyAsync(d + off_scores, scores, nBK * 4, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && noise) e = cudaMemcpyAsync(d + off_noise, noise, nBK * 4, cudaMemcpyHostToDevice, st);
@@ -1111,7 +1148,6 @@ int vodb_sample(int device, const float* scores, const uint8_t* labels, const fl
   }
   if (e == cudaSuccess && rc == VODB_OK) e = cudaMemcpyAsync(out_lse, d + off_lse, (size_t)B * 8, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d);
   if (e != cudaSuccess) {
     set_error("vodb_sample: %s", cudaGetErrorString(e));
     return VODB_ECUDA;
