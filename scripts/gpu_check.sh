@@ -21,6 +21,10 @@ if [[ $STEP == all || $STEP == tests ]]; then
   run t_merge 600 python -m pytest tests/test_merge_gpu.py -q -m gpu --timeout=300 -p no:cacheprovider
   run t_fullsize 1200 python -m pytest tests/test_fullsize_gpu.py -q -m gpu --timeout=600 -p no:cacheprovider
 fi
+if [[ $STEP == all || $STEP == driver ]]; then
+  # exactly what the driver runs at round end: one pytest process over the whole gpu suite
+  run t_driver 1800 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider
+fi
 if [[ $STEP == all || $STEP == bench ]]; then
   run bench 900 python bench.py --steps 20 --warmup 5
   run bench_ref 600 python bench.py --impl reference --steps 5 --warmup 2

@@ -6,9 +6,9 @@ out = []; A = out.append
 A("# Round 1 — profile summary (B200, sm_100a)\n")
 A("All numbers from `gpurun` boxes (1x B200 unless noted). Peaks: `MEASURED_PEAKS.json` — HBM 6534.8 GB/s (copy kernel), bf16 1671.7 TFLOP/s burst / 1404.1 sustained (cuBLAS). Workload: BASELINE configs[1], 10M x 768 bf16, exact top-100. Box-to-box variation of the same build is about +-4% (2.19-2.29 ms for the 64-query step).\n")
 A("Files: `r01a_*` first working tcgen05 path; `r01b_*` dump mode + staged survivors; `r01c..g_*` bench lines along the way; `r01h_*` final state of the round (launch list, `ncu --set full` raw pages of `score_tc_kernel<64,1>` and the 2-CTA `score_tc2_kernel`, bench lines of both arms); `r01i_*` multi-GPU bench lines with the flag/fence exchange; `r01j_*` final bench lines of the round (1 GPU both arms, 2/4/8 GPUs with the epoch-tagged LL exchange, 8 GPUs NCCL); `r01k_*` BASELINE configs[2] at full size (100M x 768 fp16 over 2/4/8 GPUs, top-1000), `ncu --set full` raw page of the kernels beside the tensor-core scan, latency probe; probes: `r01_schedule_sweep.jsonl`, `r01_query_terms_probe.json`, `r01_configs_3_5_probe.json`, `r01_compute_sanitizer.txt`. Regenerate this file with `python scripts/make_profile_summary.py`.\n")
-d = bench("r01h_bench.json"); f = bench("r01f_bench.json")
-A("## Headline (r01h_bench.json; r01f_bench.json is the same build on another box)\n")
-A("| quantity | r01h | r01f |\n|---|---|---|")
+d = bench("r01l_bench.json"); f = bench("r01h_bench.json")
+A("## Headline (r01l_bench.json = final build of the round; r01h_bench.json = the build the ncu captures below were taken from, another box)\n")
+A("| quantity | r01l | r01h |\n|---|---|---|")
 A(f"| 64-query batches, inputs resident in HBM: queries/s (ms/step) | {d['value']:.0f} ({d['ms_per_step']:.4f}) | {f['value']:.0f} ({f['ms_per_step']:.4f}) |")
 A(f"| corpus scanned, whole step | {d['corpus_gb_per_s']:.0f} GB/s = {d['roofline']['whole_step_frac']*100:.1f}% of measured HBM peak | {f['corpus_gb_per_s']:.0f} GB/s = {f['roofline']['whole_step_frac']*100:.1f}% |")
 A(f"| scoring kernel alone (CUDA events around its launches) | {d['roofline']['score_kernel_ms_per_search']:.4f} ms = {d['roofline']['achieved']:.0f} GB/s = {d['roofline']['frac']*100:.1f}% | {f['roofline']['score_kernel_ms_per_search']:.4f} ms = {f['roofline']['achieved']:.0f} GB/s = {f['roofline']['frac']*100:.1f}% |")
@@ -16,9 +16,12 @@ A(f"| select kernels per search | {d['roofline']['select_kernel_ms_per_search']*
 A(f"| e2e through `B200SearchClient.search(np.ndarray)` (pinned H2D 196 KB + D2H 77 KB inside): queries/s (ms) | {d['e2e']['value']:.0f} ({d['e2e']['ms_per_step']:.3f}) | {f['e2e']['value']:.0f} ({f['e2e']['ms_per_step']:.3f}) |")
 A(f"| per-call latency p10 / p50 / p90 (ms) | {d['latency']['p10']:.3f} / {d['latency']['p50']:.3f} / {d['latency']['p90']:.3f} | {f['latency']['p10']:.3f} / {f['latency']['p50']:.3f} / {f['latency']['p90']:.3f} |")
 c4 = d['config4_retrieve_and_sample']
-A(f"| config 4 chain (32 queries -> top-1000 -> sample 8, host in, [32,8] out) | p50 {c4['chain_ms_p50']:.3f} ms; sampler kernel p50 {c4['sampler_kernel_us_p50']:.1f} us | - |")
+c4f = f['config4_retrieve_and_sample']
+A(f"| config 4 chain (32 queries -> top-1000 -> sample 8, host in, [32,8] out; one `vodb_retrieve_sample` call in r01l) | p50 {c4['chain_ms_p50']:.3f} ms; sampler kernel p50 {c4['sampler_kernel_us_p50']:.1f} us; `sample_search_results` on host arrays p50 {c4['sample_search_results_host_call_ms_p50']*1e3:.0f} us | p50 {c4f['chain_ms_p50']:.3f} ms |")
+w = c4['dataloader_workers']
+A(f"| config 4 as {w['workers']} DataLoader worker processes see it (32-query top-1000 requests over the Unix socket) | {w['coalesced']:.0f} queries/s with shared scans ({w['requests_served']} requests in {w['scans_issued']} scans) vs {w['one_scan_per_request']:.0f} one scan per request | - |")
 lb, lf = d['large_batch'], f['large_batch']
-A(f"| 8192-query batches: queries/s (ms/step) | {lb['value']:.0f} ({lb['ms_per_step']:.1f}) 2-CTA kernel | {lf['value']:.0f} ({lf['ms_per_step']:.1f}) 1-CTA kernel |")
+A(f"| 8192-query batches (2-CTA kernel): queries/s (ms/step) | {lb['value']:.0f} ({lb['ms_per_step']:.1f}) | {lf['value']:.0f} ({lf['ms_per_step']:.1f}) |")
 A(f"| 8192-query scoring kernels | {lb['roofline']['achieved']:.0f} TFLOP/s = {lb['roofline']['frac']*100:.1f}% of burst peak, {lb['roofline']['frac_of_sustained']*100:.1f}% of sustained | {lf['roofline']['achieved']:.0f} TFLOP/s = {lf['roofline']['frac']*100:.1f}% |")
 A(f"| CPU baseline (oracle port: numpy/OpenBLAS sgemm + exact top-k, {d['cpu_baseline']['cores']} host cores, 500k-row sample x20) | {d['cpu_baseline']['value']:.1f} queries/s | - |")
 A(f"| kernels per 64-query search | {d['gpu_launches_per_step']} (prepare + 4 x (score, select)), all launched with PDL | |")
