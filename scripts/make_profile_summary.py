@@ -110,7 +110,7 @@ A("| queries | exact (CUDA cores) ms | tensor3 ms (speed-up; GB/s of fp32 bytes;
 for nq in (64, 256, 1024):
     e = fp[f'q{nq}_exact_ms']; t3 = fp[f'q{nq}_tensor3_ms']
     A(f"| {nq} | {e:.2f} | {t3:.2f} ({e/t3:.1f}x; {fp[f'q{nq}_tensor3_GBps_of_fp32_bytes']:.0f}; {fp[f'q{nq}_tensor3_recall_vs_exact']:.5f}) | {fp[f'q{nq}_tensor2_ms']:.2f} ({fp[f'q{nq}_tensor2_recall_vs_exact']:.5f}) | {fp[f'q{nq}_tensor_ms']:.2f} ({fp[f'q{nq}_tensor_recall_vs_exact']:.4f}) |")
-A("\ntensor3 reads 6 bytes per stored element (three bf16 planes) and issues 6 MMAs per K step; at 64 queries it runs at 80% of the HBM time of those 18.4 GB. Scores agree with a float64 re-score to <= 4e-6 relative (two accumulators per item: leading product / corrections).\n")
+A("\ntensor3 reads 6 bytes per stored element (three bf16 planes); up to 64 queries one MMA per plane and K step covers all query terms (N = 192 / 128 / 64), and the search runs at about 90% of the HBM time of those 18.4 GB. Scores agree with a float64 re-score to <= 4e-6 relative (leading product and corrections are accumulated in separate TMEM column groups).\n")
 A("## Epilogue history (8192-query batch, segment with ~19 survivors per 128x256 item)\n")
 A("| version | that segment | whole batch |\n|---|---|---|")
 A("| r01a: warp-aggregated global atomic per surviving column, L2 round trip inside the epilogue | 93 ms, 20% of the MMA rate | 190.5 ms, 39.7% of peak |")

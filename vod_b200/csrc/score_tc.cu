@@ -250,20 +250,29 @@ __device__ __forceinline__ void epilogue_begin_item(const TcParams& p, WarpStage
 
 // the BN score columns of this thread's corpus row: dump them (first segment) or filter against tau and push the
 // rare survivors into the warp's staging buffer
-// DUAL: the score is the sum of two accumulators, columns [0, BN) (leading product) and [BN, 2 BN) (corrections)
-template <int BN, bool DUAL = false>
+// GROUPS > 1: the score is the sum of GROUPS accumulator column groups BN apart — [0, BN) holds the leading product,
+// the others the corrections, which are summed first and added to the leading product last
+template <int BN, int GROUPS = 1>
 __device__ __forceinline__ void epilogue_columns(const TcParams& p, WarpStage& ws, const float* tau_cur,
                                                  uint32_t taddr0, int64_t row, bool valid, int q0, int sb) {
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     uint32_t v[32];
     tmem_ld_32x32b_x32(taddr0 + (uint32_t)c0, v);
-    if constexpr (DUAL) {
+    if constexpr (GROUPS == 2) {
       uint32_t w[32];
       tmem_ld_32x32b_x32(taddr0 + (uint32_t)(BN + c0), w);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(w[j])));
+    } else if constexpr (GROUPS == 3) {
+      uint32_t w[32], x[32];
+      tmem_ld_32x32b_x32(taddr0 + (uint32_t)(BN + c0), w);
+      tmem_ld_32x32b_x32(taddr0 + (uint32_t)(2 * BN + c0), x);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __fadd_rn(__uint_as_float(w[j]), __uint_as_float(x[j]))));
     } else {
       tmem_ld_wait();
     }
@@ -340,8 +349,14 @@ struct TcConfig {
   static constexpr uint32_t kBBytes = BN * KC * 2;          // one term
   static constexpr uint32_t kStageBytes = kABytes + T * kBBytes;
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
-  static constexpr bool kDual = (T > 1);
-  static constexpr uint32_t kAccCols = (kDual ? 2 : 1) * BN;  // TMEM columns of one accumulator buffer
+  // kConcat: the T query boxes of a stage sit back to back in shared memory, i.e. they ARE one K-major tile of T*BN
+  // rows, so ONE MMA with N = T*BN multiplies the corpus tile with all terms at once and every term gets its own
+  // accumulator column group: a third of the MMAs and of the corpus-tile reads of the one-MMA-per-term form, which
+  // is what keeps 3-term searches of <= 64 queries HBM-bound. Needs T*BN <= 256 (UMMA N) and two such buffers in TMEM.
+  static constexpr bool kConcat = (T > 1) && (T * BN <= 256);
+  static constexpr bool kDual = (T > 1) && !kConcat;          // one MMA per term, leading / correction accumulators
+  static constexpr int kGroups = kConcat ? T : (kDual ? 2 : 1);
+  static constexpr uint32_t kAccCols = kGroups * BN;          // TMEM columns of one accumulator buffer
   static_assert(2 * kAccCols <= 512, "two accumulator buffers must fit the 512 TMEM columns");
   static constexpr uint32_t kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
                                         : (2 * kAccCols <= 256) ? 256 : 512;
@@ -449,16 +464,28 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
             mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
             tcgen05_fence_after();
             const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+            if constexpr (Cfg::kConcat) {
+              // one MMA per K step over the nt stacked query boxes (N = nt * BN). Plane 0 fills every column group
+              // (group t = c_0 * q_t); the later planes land one group further right, so that group 0 stays the
+              // leading product c_0 * q_0 alone (truncation bias, see TcConfig) and the corrections share groups 1..
+              const uint64_t db = make_desc_sw128(smem_u32(smem_b + (stage * T) * Cfg::kBBytes));
+              const uint32_t idesc = (p.idesc & ~(0x3fu << 17)) | ((uint32_t)((BN * nt) >> 3) << 17);
+              const uint32_t d = tmem_d + (pl == 0 ? 0u : (uint32_t)BN);
 #pragma unroll
-            for (int t = 0; t < nt; ++t) {
-              const uint64_t db = make_desc_sw128(smem_u32(smem_b + (stage * T + t) * Cfg::kBBytes));
+              for (int k = 0; k < KC / UMMA_K; ++k)
+                umma_f16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | pl | k) != 0 ? 1u : 0u);
+            } else {
 #pragma unroll
-              for (int k = 0; k < KC / UMMA_K; ++k) {
-                // advance 32 bytes (16 elements) inside the 128-byte swizzle atom: +2 in the >>4 address field
-                const bool lead = (pl == 0 && t == 0);
-                const bool first = (kc | k) == 0 && (lead || (pl == 0 && t == 1));  // first MMA into its accumulator
-                umma_f16(lead ? tmem_d : tmem_d + (uint32_t)BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
-                         first ? 0u : 1u);
+              for (int t = 0; t < nt; ++t) {
+                const uint64_t db = make_desc_sw128(smem_u32(smem_b + (stage * T + t) * Cfg::kBBytes));
+#pragma unroll
+                for (int k = 0; k < KC / UMMA_K; ++k) {
+                  // advance 32 bytes (16 elements) inside the 128-byte swizzle atom: +2 in the >>4 address field
+                  const bool lead = (pl == 0 && t == 0);
+                  const bool first = (kc | k) == 0 && (lead || (pl == 0 && t == 1));  // first MMA into its accumulator
+                  umma_f16(lead || !Cfg::kDual ? tmem_d : tmem_d + (uint32_t)BN, da + (uint64_t)(2 * k),
+                           db + (uint64_t)(2 * k), p.idesc, first ? 0u : 1u);
+                }
               }
             }
             umma_commit(&empty_bar[stage]);  // frees the smem stage once the MMAs above have read it
@@ -492,7 +519,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * Cfg::kAccCols;
-      epilogue_columns<BN, Cfg::kDual>(p, ws, tau_cur, taddr0, row, valid, q0, sb);
+      epilogue_columns<BN, Cfg::kGroups>(p, ws, tau_cur, taddr0, row, valid, q0, sb);
       // all TMEM reads of this buffer are complete (wait::ld above): hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
