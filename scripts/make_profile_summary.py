@@ -124,7 +124,8 @@ A("## Query-term modes (r01_query_terms_probe.json; 10M x 768 bf16, float32 quer
 A("| mode | 64-query ms | 8192-query ms | recall@100 vs fp32 CUDA-core kernel |\n|---|---|---|---|")
 for m in ('tensor', 'tensor2', 'tensor3'):
     A(f"| {m} | {t[m+'_q64_ms']:.3f} | {t[m+'_q8192_ms']:.1f} | {t[m+'_recall_vs_exact']:.4f} |")
-A(f"| exact (fp32 FMA, CUDA cores) | {t['exact_q64_ms']:.2f} | - | 1 |\n")
+A(f"| exact (fp32 FMA, CUDA cores) | {t['exact_q64_ms']:.2f} | - | 1 |")
+A(f"| tensor3, float32 queries that are exact in bf16 (empty correction terms skipped on the device) | {t['tensor3_q64_bf16_exact_queries_ms']:.3f} (tensor on the same batch: {t['tensor_q64_bf16_exact_queries_ms']:.3f}; identical results: {t['tensor3_equals_tensor_on_bf16_exact_queries']}) | - | - |\n")
 c = json.loads((P / 'r01_configs_3_5_probe.json').read_text().strip().splitlines()[-1])
 A("## BASELINE configs 3 and 5, one GPU's share (r01_configs_3_5_probe.json, scripts/probe_configs.py)\n")
 A("| config | result |\n|---|---|")

@@ -342,6 +342,28 @@ def test_fp32_store_tensor_modes_bit_exact_on_integer_data(mode, n, d, nq, k):
     st.close()
 
 
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+def test_empty_correction_terms_are_skipped_without_changing_results(dtype):
+    """float32 queries that are exact in the store dtype have empty correction terms: the multi-term modes then run
+    the one-term computation (decided on the device, per batch) and must return exactly what `tensor` returns; one
+    inexact query in the batch switches the full computation back on."""
+    rng = np.random.default_rng(31)
+    xb = round_to(rng.standard_normal((60_000, 320), dtype=np.float32), dtype)
+    st = _store(xb, dtype)
+    for nq in (40, 100, 200):
+        xq = round_to(rng.standard_normal((nq, 320), dtype=np.float32), dtype)
+        s1, i1 = st.search(xq, 50, mode="tensor")
+        for mode in ("tensor2", "tensor3"):
+            s, i = st.search(xq, 50, mode=mode)
+            assert np.array_equal(i, i1) and np.array_equal(s, s1), (nq, mode)
+        xq[nq // 2] = rng.standard_normal(320, dtype=np.float32)       # not representable: corrections needed again
+        s3, i3 = st.search(xq, 50, mode="tensor3")
+        rs, ri = flat_ip.search(xb, xq, 50)
+        rep = flat_ip.compare_topk(xb, xq, s3, i3, rs, ri, rtol=RTOL)
+        assert rep["ok"], rep
+    st.close()
+
+
 def test_stale_query_staging_rows_never_reach_the_filter():
     """Regression: a 9-query tensor-mode search right after a 64-query exact-mode search. The staging rows 9..63
     still hold the float32 bit patterns of the earlier batch, which read as bf16 include inf / NaN; they must be

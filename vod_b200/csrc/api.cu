@@ -105,7 +105,7 @@ __global__ void convert_rows_kernel(const S* __restrict__ src, int src_dim, D* _
 template <typename S, typename D>
 __global__ void prepare_kernel(const S* __restrict__ src, int src_dim, D* __restrict__ dst, int dst_pitch, int64_t n,
                                int64_t plane_rows, int64_t fill_rows, int terms, int* __restrict__ cnt,
-                               float* __restrict__ tau, int first_rows) {
+                               float* __restrict__ tau, int first_rows, int* __restrict__ term_any) {
   pdl_launch_dependents();
   pdl_wait();  // the previous search on this stream may still be reading the staging buffer / lists
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,6 +117,7 @@ __global__ void prepare_kernel(const S* __restrict__ src, int src_dim, D* __rest
   // (possibly inf / NaN bit patterns of another dtype) never reaches the MMAs — a garbage +inf score would pass the
   // `score >= tau` filter of an unused column even against tau = +inf
   int64_t total = fill_rows * dst_pitch;
+  int nonzero = 0;  // bit t: this thread wrote a nonzero element of term t
   for (int64_t e = gtid; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = e / dst_pitch;
     int c = (int)(e - r * dst_pitch);
@@ -124,9 +125,15 @@ __global__ void prepare_kernel(const S* __restrict__ src, int src_dim, D* __rest
     for (int t = 0; t < terms; ++t) {
       D d = from_f32<D>(v);
       dst[(size_t)t * plane_rows * dst_pitch + e] = d;
-      v = __fsub_rn(v, to_f32<D>(d));
+      const float dv = to_f32<D>(d);
+      nonzero |= (dv != 0.0f) ? (1 << t) : 0;
+      v = __fsub_rn(v, dv);
     }
   }
+  // which terms carry anything at all: float32 queries that are exactly representable in the store dtype (encoder
+  // outputs computed in bf16 / fp16 and widened) have empty correction terms, and the scoring kernel skips them
+  const int any1 = __syncthreads_or(nonzero & 2), any2 = __syncthreads_or(nonzero & 4);  // logical ORs over the block
+  if (threadIdx.x == 0) term_any[blockIdx.x] = 1 | (any1 ? 2 : 0) | (any2 ? 4 : 0);
 }
 
 // fp32 store -> 3 bf16 planes with row = p0 + p1 + p2 exactly: p_i = bf16_rn(what p_0..p_{i-1} left), the remainders
@@ -242,18 +249,24 @@ int launch_convert_rows(const void* src, int src_dtype, int src_dim, void* dst, 
 namespace {
 template <typename S>
 int prepare_dispatch_dst(const void* src, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
-                         int64_t plane_rows, int terms, int* cnt, float* tau, int first_rows, cudaStream_t st) {
+                         int64_t plane_rows, int terms, int* cnt, float* tau, int first_rows, int* term_any,
+                         int* term_blocks, cudaStream_t st) {
   // query tiles are 64, 128 or 256 rows (score_tc.cu launch_score_tensor): clear the rest of the last one
   const int64_t fill_rows = std::min<int64_t>(plane_rows, n <= 64 ? 64 : n <= 128 ? 128 : (n + 255) / 256 * 256);
   int64_t total = fill_rows * dst_pitch;
   if (n == 0) return VODB_OK;
   int g = std::max(grid_for(total), (int)((n + 255) / 256));  // every query needs a thread for the list reset
+  if (g > kTermSlots) {
+    set_error("launch_prepare: %lld queries need %d blocks (> %d)", (long long)n, g, kTermSlots);
+    return VODB_EINVAL;
+  }
+  *term_blocks = g;
   const S* s = reinterpret_cast<const S*>(src);
   cudaError_t e;
   switch (dst_dtype) {
-    case VODB_F32: e = launch_pdl(prepare_kernel<S, float>, dim3(g), dim3(256), 0, st, s, src_dim, (float*)dst, dst_pitch, n, plane_rows, fill_rows, 1, cnt, tau, first_rows); break;
-    case VODB_BF16: e = launch_pdl(prepare_kernel<S, __nv_bfloat16>, dim3(g), dim3(256), 0, st, s, src_dim, (__nv_bfloat16*)dst, dst_pitch, n, plane_rows, fill_rows, terms, cnt, tau, first_rows); break;
-    case VODB_F16: e = launch_pdl(prepare_kernel<S, __half>, dim3(g), dim3(256), 0, st, s, src_dim, (__half*)dst, dst_pitch, n, plane_rows, fill_rows, terms, cnt, tau, first_rows); break;
+    case VODB_F32: e = launch_pdl(prepare_kernel<S, float>, dim3(g), dim3(256), 0, st, s, src_dim, (float*)dst, dst_pitch, n, plane_rows, fill_rows, 1, cnt, tau, first_rows, term_any); break;
+    case VODB_BF16: e = launch_pdl(prepare_kernel<S, __nv_bfloat16>, dim3(g), dim3(256), 0, st, s, src_dim, (__nv_bfloat16*)dst, dst_pitch, n, plane_rows, fill_rows, terms, cnt, tau, first_rows, term_any); break;
+    case VODB_F16: e = launch_pdl(prepare_kernel<S, __half>, dim3(g), dim3(256), 0, st, s, src_dim, (__half*)dst, dst_pitch, n, plane_rows, fill_rows, terms, cnt, tau, first_rows, term_any); break;
     default: set_error("launch_prepare: bad destination dtype %d", dst_dtype); return VODB_EINVAL;
   }
   VODB_CUDA_CHECK(e);
@@ -262,11 +275,12 @@ int prepare_dispatch_dst(const void* src, int src_dim, void* dst, int dst_dtype,
 }  // namespace
 
 int launch_prepare(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
-                   int64_t plane_rows, int terms, int* cnt, float* tau, int first_rows, cudaStream_t st) {
+                   int64_t plane_rows, int terms, int* cnt, float* tau, int first_rows, int* term_any, int* term_blocks,
+                   cudaStream_t st) {
   switch (src_dtype) {
-    case VODB_F32: return prepare_dispatch_dst<float>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows, st);
-    case VODB_BF16: return prepare_dispatch_dst<__nv_bfloat16>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows, st);
-    case VODB_F16: return prepare_dispatch_dst<__half>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows, st);
+    case VODB_F32: return prepare_dispatch_dst<float>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows, term_any, term_blocks, st);
+    case VODB_BF16: return prepare_dispatch_dst<__nv_bfloat16>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows, term_any, term_blocks, st);
+    case VODB_F16: return prepare_dispatch_dst<__half>(src, src_dim, dst, dst_dtype, dst_pitch, n, plane_rows, terms, cnt, tau, first_rows, term_any, term_blocks, st);
   }
   set_error("bad src dtype %d", src_dtype);
   return VODB_EINVAL;
@@ -360,6 +374,7 @@ int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes) {
   w.cap = cap;
   if (!w.overflow) {
     VODB_CUDA_CHECK(cudaMalloc(&w.overflow, sizeof(int)));
+    VODB_CUDA_CHECK(cudaMalloc(&w.term_any, kTermSlots * sizeof(int)));
     VODB_CUDA_CHECK(cudaMemset(w.overflow, 0, sizeof(int)));
     VODB_CUDA_CHECK(cudaMallocHost(&w.overflow_host, sizeof(int)));
   }
@@ -393,7 +408,7 @@ int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes) {
 }
 
 void free_workspace(Workspace& w) {
-  cudaFree(w.cand_s); cudaFree(w.cand_i); cudaFree(w.cnt); cudaFree(w.tau); cudaFree(w.overflow);
+  cudaFree(w.cand_s); cudaFree(w.cand_i); cudaFree(w.cnt); cudaFree(w.tau); cudaFree(w.overflow); cudaFree(w.term_any);
   if (w.overflow_host) cudaFreeHost(w.overflow_host);
   cudaFree(w.q_stage); cudaFree(w.q_in); cudaFree(w.out_pack); cudaFree(w.chain_dev);
   if (w.out_host) cudaFreeHost(w.out_host);
@@ -478,12 +493,13 @@ int run_scan(vodb_store* s, const void* q_dev, int q_dtype, int nq, int k, int m
   // lists; the first segment (dump mode) stores every score, so cnt starts at its row count
   const int64_t rows_pad = ((int64_t)nq + 255) / 256 * 256;
   const bool tensor = is_tensor_mode(mode);
+  int term_blocks = 0;
   const bool planes = tensor && s->dtype == VODB_F32;   // fp32 store: bf16 planes x bf16 query terms
   const int tc_dtype = planes ? VODB_BF16 : s->dtype;   // what the tensor-core kernel multiplies
   int rc = planes ? ensure_planes(s, st) : VODB_OK;
   if (rc != VODB_OK) return rc;
   rc = launch_prepare(q_dev, q_dtype, s->dim, w.q_stage, tensor ? tc_dtype : VODB_F32, s->pitch, nq, rows_pad,
-                      tensor ? mode_terms(mode) : 1, w.cnt, w.tau, (int)(b[1] - b[0]), st);
+                      tensor ? mode_terms(mode) : 1, w.cnt, w.tau, (int)(b[1] - b[0]), w.term_any, &term_blocks, st);
   if (rc != VODB_OK) return rc;
   int64_t launches = 1;
   for (size_t i = 0; i + 1 < b.size(); ++i) {
@@ -504,6 +520,8 @@ int run_scan(vodb_store* s, const void* q_dev, int q_dtype, int nq, int k, int m
     a.dump = (i == 0);
     a.terms = tensor ? mode_terms(mode) : 1;
     a.planes = planes ? a.terms : 1;
+    a.term_any = w.term_any;
+    a.term_blocks = term_blocks;
     ProfileState* prof = s->profiling ? static_cast<ProfileState*>(s->prof) : nullptr;
     if (prof) cudaEventRecord(prof->next(), st);
     rc = is_tensor_mode(mode) ? launch_score_tensor(s, a, st) : launch_score_exact(a, s->sm_count, st);

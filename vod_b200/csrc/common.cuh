@@ -107,6 +107,7 @@ struct Workspace {
   int32_t* cand_i = nullptr;
   int* cnt = nullptr;
   float* tau = nullptr;
+  int* term_any = nullptr;     // [kTermSlots] per prepare-block bit mask: bit t set = query term t has a nonzero element
   int* overflow = nullptr;     // device flag: a candidate list ran out of room
   int* overflow_host = nullptr;  // pinned mirror
   int nq_cap = 0;        // counters / thresholds allocated for this many queries
@@ -177,6 +178,8 @@ struct SegmentArgs {
   int cap;
   int terms;            // TENSOR: 16-bit terms per query (1..3), staged as [terms][round_up(nq,256)][pitch]
   int planes;           // TENSOR on an fp32 store: bf16 corpus planes used (= terms); 1 otherwise
+  const int* term_any;  // prepare kernel's per-block term masks (which query terms are nonzero at all), term_blocks of them
+  int term_blocks;
   bool dump;            // first segment of a scan: lists are empty, every score is stored at slot row-row_begin
 };
 
@@ -186,6 +189,7 @@ struct SegmentArgs {
 //   w0 = epoch<<32 | score bits, w1 = epoch<<32 | id[31:0], w2 = epoch<<32 | id[63:32].
 // An aligned 8-byte store is single-copy atomic, so a reader that sees the tag also sees the payload: no fences, no
 // flags, no counters. The merge kernel spins on the tags of the entries it needs and reduces world*k -> k.
+constexpr int kTermSlots = 148 * 32;  // upper bound of the prepare kernel's grid (api.cu grid_for)
 constexpr int kMaxPeers = 16;
 struct ExchangeDst {
   int world;
@@ -212,8 +216,10 @@ int launch_convert_rows(const void* src, int src_dtype, int src_dim, void* dst, 
                         int64_t n, cudaStream_t stream);
 // first kernel of a search: stage the queries (fp32 plane for EXACT, `terms` 16-bit planes for TENSOR) and reset the
 // candidate lists (cnt = rows of the first segment, tau = -inf) in one launch
+// `term_any[b]` receives block b's mask of nonzero terms; returns the number of blocks launched in *term_blocks
 int launch_prepare(const void* src, int src_dtype, int src_dim, void* dst, int dst_dtype, int dst_pitch, int64_t n,
-                   int64_t plane_rows, int terms, int* cnt, float* tau, int first_rows, cudaStream_t stream);
+                   int64_t plane_rows, int terms, int* cnt, float* tau, int first_rows, int* term_any, int* term_blocks,
+                   cudaStream_t stream);
 int launch_split_planes(const float* src, void* planes, int64_t row0, int64_t n, int pitch, int64_t n_rows,
                         cudaStream_t stream);
 int launch_fill_synthetic(void* dst, int dtype, int dim, int pitch, uint64_t seed, int64_t global_row0, int64_t n,

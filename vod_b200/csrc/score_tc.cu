@@ -147,6 +147,8 @@ struct TcParams {
   int cap;
   uint32_t idesc;
   int dump;  // first segment: store every score at slot (row - row_begin) instead of filtering
+  const int* term_any;  // per prepare-block masks of the query terms that are nonzero anywhere (api.cu prepare_kernel)
+  int term_blocks;
 };
 
 // Per-warp staging of filter survivors (shared memory). Each epilogue warp owns two small buffers: survivors of
@@ -252,20 +254,16 @@ __device__ __forceinline__ void epilogue_begin_item(const TcParams& p, WarpStage
 // rare survivors into the warp's staging buffer
 // GROUPS > 1: the score is the sum of GROUPS accumulator column groups BN apart — [0, BN) holds the leading product,
 // the others the corrections, which are summed first and added to the leading product last
+// `groups` (<= GROUPS, uniform over the CTA) is how many of them this launch actually wrote: correction terms that are
+// zero for the whole query batch are skipped by the producer and the MMA warp, and their columns hold nothing.
 template <int BN, int GROUPS = 1>
 __device__ __forceinline__ void epilogue_columns(const TcParams& p, WarpStage& ws, const float* tau_cur,
-                                                 uint32_t taddr0, int64_t row, bool valid, int q0, int sb) {
+                                                 uint32_t taddr0, int64_t row, bool valid, int q0, int sb, int groups) {
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     uint32_t v[32];
     tmem_ld_32x32b_x32(taddr0 + (uint32_t)c0, v);
-    if constexpr (GROUPS == 2) {
-      uint32_t w[32];
-      tmem_ld_32x32b_x32(taddr0 + (uint32_t)(BN + c0), w);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(w[j])));
-    } else if constexpr (GROUPS == 3) {
+    if (GROUPS >= 3 && groups >= 3) {
       uint32_t w[32], x[32];
       tmem_ld_32x32b_x32(taddr0 + (uint32_t)(BN + c0), w);
       tmem_ld_32x32b_x32(taddr0 + (uint32_t)(2 * BN + c0), x);
@@ -273,6 +271,12 @@ __device__ __forceinline__ void epilogue_columns(const TcParams& p, WarpStage& w
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __fadd_rn(__uint_as_float(w[j]), __uint_as_float(x[j]))));
+    } else if (GROUPS >= 2 && groups >= 2) {
+      uint32_t w[32];
+      tmem_ld_32x32b_x32(taddr0 + (uint32_t)(BN + c0), w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(w[j])));
     } else {
       tmem_ld_wait();
     }
@@ -415,6 +419,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
   pdl_wait();
 
   const int n_items = p.n_ctiles * p.n_qtiles;
+  // query terms in use: all T, unless the prepare kernel found the trailing correction terms empty for the whole
+  // batch (float32 queries that are exact in the store dtype) — then they are neither loaded nor multiplied, and
+  // the result is bit-identical to the full computation. Corpus planes (P > 1) always run in full.
+  int nt_run = T;
+  if constexpr (T > 1 && P == 1) {
+    int m = 0;
+    for (int i = threadIdx.x; i < p.term_blocks; i += kThreads) m |= p.term_any[i];
+    const int any1 = __syncthreads_or(m & 2), any2 = __syncthreads_or(m & 4);  // logical ORs over the CTA
+    nt_run = (T >= 3 && any2) ? 3 : any1 ? 2 : 1;
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -431,15 +445,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
         for (int kc = 0; kc < p.kchunks; ++kc) {
 #pragma unroll
           for (int pl = 0; pl < P; ++pl) {
-            const int nt = (P == 1) ? T : (P - pl);  // query terms multiplied with this plane
+            const int nt = (P == 1) ? nt_run : (P - pl);  // query terms multiplied with this plane
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], Cfg::kABytes + (uint32_t)nt * Cfg::kBBytes);
             tma_load_2d(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC,
                         pl * p.plane_rows + row0, corpus_policy);
 #pragma unroll
-            for (int t = 0; t < nt; ++t)
-              tma_load_2d(&tmap_query, &full_bar[stage], smem_b + (stage * T + t) * Cfg::kBBytes, kc * KC,
-                          t * p.q_rows_pad + q0, kEvictLast);
+            for (int t = 0; t < T; ++t)
+              if (t < nt)
+                tma_load_2d(&tmap_query, &full_bar[stage], smem_b + (stage * T + t) * Cfg::kBBytes, kc * KC,
+                            t * p.q_rows_pad + q0, kEvictLast);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -460,7 +475,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
         for (int kc = 0; kc < p.kchunks; ++kc) {
 #pragma unroll
           for (int pl = 0; pl < P; ++pl) {
-            const int nt = (P == 1) ? T : (P - pl);
+            const int nt = (P == 1) ? nt_run : (P - pl);
             mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
             tcgen05_fence_after();
             const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
@@ -476,7 +491,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
                 umma_f16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | pl | k) != 0 ? 1u : 0u);
             } else {
 #pragma unroll
-              for (int t = 0; t < nt; ++t) {
+              for (int t = 0; t < T; ++t) {
+                if (t >= nt) break;
                 const uint64_t db = make_desc_sw128(smem_u32(smem_b + (stage * T + t) * Cfg::kBBytes));
 #pragma unroll
                 for (int k = 0; k < KC / UMMA_K; ++k) {
@@ -519,7 +535,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * Cfg::kAccCols;
-      epilogue_columns<BN, Cfg::kGroups>(p, ws, tau_cur, taddr0, row, valid, q0, sb);
+      epilogue_columns<BN, Cfg::kGroups>(p, ws, tau_cur, taddr0, row, valid, q0, sb,
+                                          P == 1 ? (Cfg::kConcat ? nt_run : (nt_run > 1 ? 2 : 1)) : Cfg::kGroups);
       // all TMEM reads of this buffer are complete (wait::ld above): hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
@@ -739,7 +756,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_columns<BN>(p, ws, tau_cur, taddr0, row, valid, q0, sb);
+      epilogue_columns<BN>(p, ws, tau_cur, taddr0, row, valid, q0, sb, 1);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cta(&tempty_bar[acc], 0);  // the leader's barrier collects both CTAs' epilogues
@@ -849,6 +866,8 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.overflow = a.overflow;
   p.cap = a.cap;
   p.dump = a.dump ? 1 : 0;
+  p.term_any = a.term_any;
+  p.term_blocks = a.term_blocks;
   const uint32_t fmt = (a.dtype == VODB_BF16) ? 1u : 0u;  // UMMA F16F32Format: F16=0, BF16=1
   p.idesc = (1u << 4) /*D=f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
@@ -885,6 +904,8 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.overflow = a.overflow;
   p.cap = a.cap;
   p.dump = a.dump ? 1 : 0;
+  p.term_any = nullptr;
+  p.term_blocks = 0;
   const uint32_t fmt = (a.dtype == VODB_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cfg::BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
