@@ -149,7 +149,12 @@ struct TcParams {
   int dump;  // first segment: store every score at slot (row - row_begin) instead of filtering
   const int* term_any;  // per prepare-block masks of the query terms that are nonzero anywhere (api.cu prepare_kernel)
   int term_blocks;
+  // Large multi-term batches are launched twice: the 2-CTA one-term kernel with kOnlyIfSingleTerm and the multi-term
+  // kernel with kOnlyIfMultiTerm. Exactly one of them does the work, chosen on the device from term_any; the other
+  // finds zero items and retires in a few microseconds.
+  int term_policy;
 };
+constexpr int kTermAlways = 0, kOnlyIfSingleTerm = 1, kOnlyIfMultiTerm = 2;
 
 // Per-warp staging of filter survivors (shared memory). Each epilogue warp owns two small buffers: survivors of
 // item i are pushed with shared-memory atomics into buffer i&1 and appended to the global per-query lists at the
@@ -418,7 +423,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
   pdl_launch_dependents();
   pdl_wait();
 
-  const int n_items = p.n_ctiles * p.n_qtiles;
+  int n_items = p.n_ctiles * p.n_qtiles;
   // query terms in use: all T, unless the prepare kernel found the trailing correction terms empty for the whole
   // batch (float32 queries that are exact in the store dtype) — then they are neither loaded nor multiplied, and
   // the result is bit-identical to the full computation. Corpus planes (P > 1) always run in full.
@@ -428,6 +433,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
     for (int i = threadIdx.x; i < p.term_blocks; i += kThreads) m |= p.term_any[i];
     const int any1 = __syncthreads_or(m & 2), any2 = __syncthreads_or(m & 4);  // logical ORs over the CTA
     nt_run = (T >= 3 && any2) ? 3 : any1 ? 2 : 1;
+    if (p.term_policy == kOnlyIfMultiTerm && nt_run == 1) n_items = 0;  // the one-term pair kernel has this batch
   }
 
   if (warp == 0) {
@@ -684,7 +690,12 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
 
   const int n_pairs = gridDim.x >> 1;
   const int pair = blockIdx.x >> 1;
-  const int n_items = p.n_ctiles * p.n_qtiles;  // n_ctiles counts 256-row pair tiles here
+  int n_items = p.n_ctiles * p.n_qtiles;  // n_ctiles counts 256-row pair tiles here
+  if (p.term_policy == kOnlyIfSingleTerm) {   // uniform over the grid: every CTA reads the same masks
+    int m = 0;
+    for (int i = threadIdx.x; i < p.term_blocks; i += kThreads) m |= p.term_any[i];
+    if (__syncthreads_or(m & 2)) n_items = 0;  // correction terms present: the multi-term kernel has this batch
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -820,6 +831,18 @@ int encode_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int p
   return VODB_OK;
 }
 
+// the 2-CTA kernel serves large single-term batches; VODB_TC2=0 forces the 1-CTA kernel (A/B comparisons)
+bool pair_kernel_enabled() {
+  static const char* env = std::getenv("VODB_TC2");
+  return env ? (env[0] != '0') : true;
+}
+bool use_pair_kernel(const SegmentArgs& a) { return pair_kernel_enabled() && a.terms == 1 && a.planes == 1 && a.nq > 128; }
+// large multi-term batches on a 16-bit store: the pair kernel also runs, for the case that the correction terms
+// turn out empty on the device (see TcParams::term_policy)
+bool use_pair_kernel_for_single_term(const SegmentArgs& a) {
+  return pair_kernel_enabled() && a.terms > 1 && a.planes == 1 && a.nq > 128;
+}
+
 // corpus tensor map (cached in the store): the rows themselves (bf16 / fp16 store), or the bf16 planes of an fp32
 // store stacked along the rows ([3 * n_rows, pitch]; plane p of row r is row p * n_rows + r)
 int corpus_tensor_map(vodb_store* s, const CUtensorMap** out) {
@@ -868,6 +891,7 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.dump = a.dump ? 1 : 0;
   p.term_any = a.term_any;
   p.term_blocks = a.term_blocks;
+  p.term_policy = (T > 1 && P == 1 && use_pair_kernel_for_single_term(a)) ? kOnlyIfMultiTerm : kTermAlways;
   const uint32_t fmt = (a.dtype == VODB_BF16) ? 1u : 0u;  // UMMA F16F32Format: F16=0, BF16=1
   p.idesc = (1u << 4) /*D=f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
@@ -904,8 +928,9 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.overflow = a.overflow;
   p.cap = a.cap;
   p.dump = a.dump ? 1 : 0;
-  p.term_any = nullptr;
-  p.term_blocks = 0;
+  p.term_any = a.term_any;
+  p.term_blocks = a.term_blocks;
+  p.term_policy = (a.terms > 1) ? kOnlyIfSingleTerm : kTermAlways;
   const uint32_t fmt = (a.dtype == VODB_BF16) ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cfg::BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
@@ -927,13 +952,6 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   cfg.numAttrs = 2;
   VODB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, score_tc2_kernel, *tmap_store, tmap_q, p));
   return VODB_OK;
-}
-
-// the 2-CTA kernel serves large single-term batches; VODB_TC2=0 forces the 1-CTA kernel (A/B comparisons)
-bool use_pair_kernel(const SegmentArgs& a) {
-  static const char* env = std::getenv("VODB_TC2");
-  const bool enabled = env ? (env[0] != '0') : true;
-  return enabled && a.terms == 1 && a.planes == 1 && a.nq > 128;
 }
 
 }  // namespace
@@ -961,6 +979,10 @@ int launch_score_tensor(vodb_store* s, const SegmentArgs& a, cudaStream_t stream
     return a.nq <= 64 ? launch_bn<64, 3, 3>(s, a, stream) : launch_bn<128, 3, 3>(s, a, stream);
   }
   if (use_pair_kernel(a)) return launch_pair(s, a, stream);
+  if (use_pair_kernel_for_single_term(a)) {
+    int rc = launch_pair(s, a, stream);  // works only if the correction terms are empty; the launch below otherwise
+    if (rc != VODB_OK) return rc;
+  }
   switch (a.terms) {
     case 1:
       if (a.nq <= 64) return launch_bn<64, 1>(s, a, stream);
