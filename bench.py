@@ -49,6 +49,7 @@ def parse_args():
     p.add_argument("--rows", type=int, default=N_ROWS, help="override the corpus size (development only)")
     p.add_argument("--no-large", action="store_true", help="skip the 8192-query section")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    p.add_argument("--no-config4", action="store_true", help="skip the retrieve-and-sample section (profiling runs)")
     p.add_argument("--large-steps", type=int, default=3)
     p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="cross-shard exchange (N>1)")
     p.add_argument("--top-k", type=int, default=TOP_K, help="results per query (BASELINE configs[2] uses 1000)")
@@ -349,7 +350,7 @@ def main():
     # ---- e2e: reference-facing client call with host buffers (pinned H2D + D2H inside the timed region) ----
     q_host = make_queries(torch, args.warmup + args.steps, Q_SMALL, "cpu", tdtype).pin_memory()
     if world == 1:
-        master = vod_b200.B200SearchMaster(store=corpus.store, mode="tensor")
+        master = vod_b200.B200SearchMaster(store=corpus.store)  # default mode: exact 3-term scoring of float32 queries
         master.__enter__()
         client = master.get_client()
 
@@ -371,7 +372,7 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": Q_SMALL * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": Q_SMALL * DIM * 4,
            "d2h_bytes_per_step": Q_SMALL * TOP_K * 12, "ms_per_step": e2e_s / args.steps * 1e3,
-           "api": "B200SearchClient.search(vector=np.ndarray[64,768] f32) -> RetrievalBatch" if world == 1
+           "api": "B200SearchClient.search(vector=np.ndarray[64,768] f32) -> RetrievalBatch, default (auto) mode" if world == 1
            else "ShardedCorpus.search_device on pinned host queries + .cpu() of the merged result"}
 
     # ---- per-call latency (search enqueue -> results ready on the device), p10 / p50 / p90 over fresh batches ----
@@ -392,7 +393,7 @@ def main():
 
     # ---- BASELINE configs[3]: RealmCollate-style chain, 32 queries -> top-1000 -> priority sampling of 8 (rank 0) ----
     config4 = None
-    if world == 1:
+    if world == 1 and not args.no_config4:
         try:
             pipe = vod_b200.DenseRetrievalSampler(corpus.store, top_k=1000, total=8, max_pos_sections=3, mode="tensor")
             q4 = make_queries(torch, 30, 32, "cpu", torch.bfloat16).pin_memory()

@@ -29,10 +29,13 @@ if [[ $STEP == all || $STEP == bench ]]; then
   run bench 900 python bench.py --steps 20 --warmup 5
   run bench_ref 600 python bench.py --impl reference --steps 5 --warmup 2
 fi
+if [[ $STEP == ncu256 ]]; then
+  run ncu_full256 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:score_tc2_kernel -s 7 -c 7 -o gpurun_out/prof_score_tc256 python bench.py --steps 1 --warmup 1 --no-cpu --no-config4 --large-steps 1
+fi
 if [[ $STEP == all || $STEP == ncu ]]; then
   run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --large-steps 1
   run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:score_tc_kernel -s 4 -c 4 -o gpurun_out/prof_score_tc python bench.py --steps 2 --warmup 1 --no-cpu --no-large
-  run ncu_full256 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:score_tc2_kernel -s 7 -c 7 -o gpurun_out/prof_score_tc256 python bench.py --steps 1 --warmup 1 --no-cpu --large-steps 1
+  run ncu_full256 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:score_tc2_kernel -s 7 -c 7 -o gpurun_out/prof_score_tc256 python bench.py --steps 1 --warmup 1 --no-cpu --no-config4 --large-steps 1
 fi
 if [[ $STEP == all || $STEP == ncu_aux ]]; then
   run ncu_aux 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:score_exact|select_kernel|merge|sample_kernel|match_labels|gather_picks' -c 60 -o gpurun_out/prof_aux python scripts/ncu_aux_probe.py

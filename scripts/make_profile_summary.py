@@ -5,10 +5,10 @@ def bench(name): return json.loads([l for l in (P / name).read_text().splitlines
 out = []; A = out.append
 A("# Round 1 — profile summary (B200, sm_100a)\n")
 A("All numbers from `gpurun` boxes (1x B200 unless noted). Peaks: `MEASURED_PEAKS.json` — HBM 6534.8 GB/s (copy kernel), bf16 1671.7 TFLOP/s burst / 1404.1 sustained (cuBLAS). Workload: BASELINE configs[1], 10M x 768 bf16, exact top-100. Box-to-box variation of the same build is about +-4% (2.19-2.29 ms for the 64-query step).\n")
-A("Files: `r01a_*` first working tcgen05 path; `r01b_*` dump mode + staged survivors; `r01c..g_*` bench lines along the way; `r01h_*` final state of the round (launch list, `ncu --set full` raw pages of `score_tc_kernel<64,1>` and the 2-CTA `score_tc2_kernel`, bench lines of both arms); `r01i_*` multi-GPU bench lines with the flag/fence exchange; `r01j_*` final bench lines of the round (1 GPU both arms, 2/4/8 GPUs with the epoch-tagged LL exchange, 8 GPUs NCCL); `r01k_*` BASELINE configs[2] at full size (100M x 768 fp16 over 2/4/8 GPUs, top-1000), `ncu --set full` raw page of the kernels beside the tensor-core scan, latency probe; probes: `r01_schedule_sweep.jsonl`, `r01_query_terms_probe.json`, `r01_configs_3_5_probe.json`, `r01_compute_sanitizer.txt`. Regenerate this file with `python scripts/make_profile_summary.py`.\n")
-d = bench("r01l_bench.json"); f = bench("r01h_bench.json")
-A("## Headline (r01l_bench.json = final build of the round; r01h_bench.json = the build the ncu captures below were taken from, another box)\n")
-A("| quantity | r01l | r01h |\n|---|---|---|")
+A("Files: `r01a_*` first working tcgen05 path; `r01b_*` dump mode + staged survivors; `r01c..g_*` bench lines along the way; `r01h_*` final state of the round (launch list, `ncu --set full` raw pages of `score_tc_kernel<64,1>` and the 2-CTA `score_tc2_kernel`, bench lines of both arms); `r01i_*` multi-GPU bench lines with the flag/fence exchange; `r01j_*` final bench lines of the round (1 GPU both arms, 2/4/8 GPUs with the epoch-tagged LL exchange, 8 GPUs NCCL); `r01l_*`/`r01m_*` bench lines, launch list and `ncu --set full` raw pages of the final build; `r01k_*` BASELINE configs[2] at full size (100M x 768 fp16 over 2/4/8 GPUs, top-1000), `ncu --set full` raw page of the kernels beside the tensor-core scan, latency probe; probes: `r01_schedule_sweep.jsonl`, `r01_query_terms_probe.json`, `r01_configs_3_5_probe.json`, `r01_compute_sanitizer.txt`. Regenerate this file with `python scripts/make_profile_summary.py`.\n")
+d = bench("r01m_bench.json"); f = bench("r01h_bench.json")
+A("## Headline (r01m_bench.json = final build of the round, same gpurun call as the r01m ncu captures below; r01h_bench.json = an earlier build on another box)\n")
+A("| quantity | r01m | r01h |\n|---|---|---|")
 A(f"| 64-query batches, inputs resident in HBM: queries/s (ms/step) | {d['value']:.0f} ({d['ms_per_step']:.4f}) | {f['value']:.0f} ({f['ms_per_step']:.4f}) |")
 A(f"| corpus scanned, whole step | {d['corpus_gb_per_s']:.0f} GB/s = {d['roofline']['whole_step_frac']*100:.1f}% of measured HBM peak | {f['corpus_gb_per_s']:.0f} GB/s = {f['roofline']['whole_step_frac']*100:.1f}% |")
 A(f"| scoring kernel alone (CUDA events around its launches) | {d['roofline']['score_kernel_ms_per_search']:.4f} ms = {d['roofline']['achieved']:.0f} GB/s = {d['roofline']['frac']*100:.1f}% | {f['roofline']['score_kernel_ms_per_search']:.4f} ms = {f['roofline']['achieved']:.0f} GB/s = {f['roofline']['frac']*100:.1f}% |")
@@ -17,7 +17,7 @@ A(f"| e2e through `B200SearchClient.search(np.ndarray)` (pinned H2D 196 KB + D2H
 A(f"| per-call latency p10 / p50 / p90 (ms) | {d['latency']['p10']:.3f} / {d['latency']['p50']:.3f} / {d['latency']['p90']:.3f} | {f['latency']['p10']:.3f} / {f['latency']['p50']:.3f} / {f['latency']['p90']:.3f} |")
 c4 = d['config4_retrieve_and_sample']
 c4f = f['config4_retrieve_and_sample']
-A(f"| config 4 chain (32 queries -> top-1000 -> sample 8, host in, [32,8] out; one `vodb_retrieve_sample` call in r01l) | p50 {c4['chain_ms_p50']:.3f} ms; sampler kernel p50 {c4['sampler_kernel_us_p50']:.1f} us; `sample_search_results` on host arrays p50 {c4['sample_search_results_host_call_ms_p50']*1e3:.0f} us | p50 {c4f['chain_ms_p50']:.3f} ms |")
+A(f"| config 4 chain (32 queries -> top-1000 -> sample 8, host in, [32,8] out; one `vodb_retrieve_sample` call in r01m) | p50 {c4['chain_ms_p50']:.3f} ms; sampler kernel p50 {c4['sampler_kernel_us_p50']:.1f} us; `sample_search_results` on host arrays p50 {c4['sample_search_results_host_call_ms_p50']*1e3:.0f} us | p50 {c4f['chain_ms_p50']:.3f} ms |")
 w = c4['dataloader_workers']
 A(f"| config 4 as {w['workers']} DataLoader worker processes see it (32-query top-1000 requests over the Unix socket) | {w['coalesced']:.0f} queries/s with shared scans ({w['requests_served']} requests in {w['scans_issued']} scans) vs {w['one_scan_per_request']:.0f} one scan per request | - |")
 lb, lf = d['large_batch'], f['large_batch']
@@ -41,12 +41,12 @@ for label, files in series:
         l = (x.get('large_batch') or {}).get('value')
         A(f"| {n} ({label}) | {ex} | {fn} | {x['value']:.0f} | {x['ms_per_step']:.4f} | {x['value']/base:.2f}x | {'%.0f' % l if l else '-'} |")
 A("")
-lines = [l for l in open(P / 'r01h_launches_ncu.csv') if not l.startswith('==')]
+lines = [l for l in open(P / 'r01m_launches_ncu.csv') if not l.startswith('==')]
 r = list(csv.DictReader(lines))
 # first complete search = first 'prepare' after the synthetic fill
 start = next(i for i, row in enumerate(r) if 'prepare_kernel' in row['Kernel Name'])
 start = next(i for i, row in enumerate(r) if 'prepare_kernel' in row['Kernel Name'] and i > start)
-A("## One 64-query search, per launch (ncu launch list r01h_launches_ncu.csv: cold cache, serialised)\n")
+A("## One 64-query search, per launch (ncu launch list r01m_launches_ncu.csv: cold cache, serialised)\n")
 A("| # | kernel | grid x block | us |\n|---|---|---|---|")
 tot = sc = 0
 for row in r[start:start + 9]:
@@ -64,9 +64,9 @@ def table(path, title, algo_rows, elt=1536):
         nrows = algo_rows[j] if j < len(algo_rows) else 0
         A(f"| {j} | {nrows} | {float(g('gpu__time_duration.sum')):.4f} | {float(g('dram__bytes_read.sum')):.3f} ({nrows*elt/1e9:.3f}) | {float(g('dram__bytes_write.sum')):.1f} | {float(g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | {float(g('TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed')):.1f} | {float(g('lts__throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | {float(g('lts__t_sector_hit_rate.pct')):.1f} | {float(g('sm__cycles_elapsed.avg.per_second')):.3f} |")
     A("")
-table('r01h_score_tc64_ncu_raw.csv', "ncu --set full, `score_tc_kernel<64,1>` (64 queries), the 4 segments of one search", [4096, 83840, 1800960, 8111104])
-A("DRAM traffic equals the algorithmic bytes (15.36 GB read per search, +0.07%): nothing is re-read, the score matrix never exists. The two large segments run at 6.9-7.0 TB/s (84-85% of ncu's DRAM peak, 106% of the copy-kernel figure) with the tensor pipe 16-20% busy: HBM-bound as designed. 128 registers, 1 CTA/SM, 192 threads.\n")
-table('r01h_score_tc2_pair_ncu_raw.csv', "ncu --set full, `score_tc2_kernel` (2-CTA pairs, 8192 queries), the 7 segments of one search", [4096, 12288, 49152, 196608, 786432, 3145728, 5805696])
+table('r01m_score_tc64_ncu_raw.csv', "ncu --set full, `score_tc_kernel<64,1,1>` (64 queries), the 4 segments of one search", [4096, 83840, 1800960, 8111104])
+A("DRAM traffic equals the algorithmic bytes (15.36 GB read per search, +0.1%): nothing is re-read, the score matrix never exists. The two large segments run at 6.9-7.0 TB/s (84-85% of ncu's DRAM peak, 106% of the copy-kernel figure) with the tensor pipe 16-20% busy: HBM-bound as designed. 128 registers, 1 CTA/SM, 192 threads.\n")
+table('r01m_score_tc2_pair_ncu_raw.csv', "ncu --set full, `score_tc2_kernel` (2-CTA pairs, 8192 queries), the 7 segments of one search", [4096, 12288, 49152, 196608, 786432, 3145728, 5805696])
 A("The large segments keep the tensor pipe 83-87% active at 1.41-1.44 GHz (sw_power_cap): the kernel sits at the MMA issue limit at the clock the 1 kW budget allows. Against the 1-CTA capture (`r01e_score_tc256_ncu_raw.csv`: 86-90% active at 1.38 GHz, L2 throughput 67-72%) the pair kernel moves 1/3 less data per flop (L2 throughput 50%), which buys the higher clock. Early segments (dense survivors, few items per pair) are below that; they cover 10% of the rows.\n")
 A("## BASELINE configs[2] at full size: 100M x 768 fp16 row-sharded over 2/4/8 B200, top-1000, fused peer-memory exchange (r01k_bench_c3_n*_p2p.json)\n")
 A("The north-star target configuration (>= 80% of the HBM roofline at 64-query batches, >= 60% of the bf16 tensor roofline at 8192-query batches). `python -m torch.distributed.run --nproc-per-node N bench.py --gpus N --rows 100000000 --top-k 1000 --store-dtype float16`.\n")
