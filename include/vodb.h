@@ -31,7 +31,8 @@
  *   - one store = one row shard on one GPU. Multi-GPU = one process per GPU,
  *     each owning one store with its `row_offset`; per-shard results are
  *     exchanged by the host code (NCCL all-gather) and reduced by vodb_merge_topk;
- *   - a store is not thread-safe: one host thread at a time.
+ *   - every call on a store takes the store's mutex, so host threads take turns; searches that are enqueued
+ *     asynchronously (out_on_device) share the store's candidate lists and must go to the same stream.
  */
 #ifndef VODB_H_
 #define VODB_H_

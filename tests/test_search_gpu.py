@@ -441,3 +441,34 @@ def test_pair_kernel_overflow_fallback_and_odd_tile_counts():
         rs, ri = flat_ip.search(xb2, xq2, 100)
         assert np.array_equal(i, ri) and np.array_equal(s, rs)
         st.close()
+
+
+@pytest.mark.timeout(300)
+def test_host_threads_share_a_store():
+    """Several host threads search one store concurrently (the store serialises them); every result is exact."""
+    import threading
+
+    rng = np.random.default_rng(77)
+    xb = int_valued(rng, (30_000, 96))
+    st = _store(xb, "bfloat16")
+    errors = []
+
+    def work(t):
+        try:
+            r = np.random.default_rng(t)
+            for _ in range(6):
+                nq, k = int(r.choice([3, 40, 130])), int(r.choice([5, 100, 700]))
+                xq = int_valued(r, (nq, 96))
+                s, i = st.search(xq, k, mode=str(r.choice(["tensor", "tensor3", "exact"])))
+                rs, ri = flat_ip.search(xb, xq, k)
+                assert np.array_equal(i, ri) and np.array_equal(s, rs)
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[0]
+    st.close()

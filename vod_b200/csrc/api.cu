@@ -705,6 +705,7 @@ void vodb_store_destroy(vodb_store* s) {
 int vodb_store_add(vodb_store* s, const void* rows, int src_dtype, int src_on_device, int64_t row0, int64_t n,
                    void* stream) {
   VODB_REQUIRE(s != nullptr, "vodb_store_add: store is NULL");
+  std::lock_guard<std::mutex> store_lock(s->mu);
   VODB_REQUIRE(n >= 0 && row0 >= 0 && row0 + n <= s->n_rows, "vodb_store_add: rows [%lld, %lld) outside the store (%lld rows)",
                (long long)row0, (long long)(row0 + n), (long long)s->n_rows);
   VODB_REQUIRE(src_dtype == VODB_F32 || src_dtype == VODB_BF16 || src_dtype == VODB_F16, "vodb_store_add: bad src dtype %d", src_dtype);
@@ -744,6 +745,7 @@ int vodb_store_add(vodb_store* s, const void* rows, int src_dtype, int src_on_de
 
 int vodb_store_fill_synthetic(vodb_store* s, uint64_t seed, int64_t row0, int64_t n, int unit_norm, void* stream) {
   VODB_REQUIRE(s != nullptr, "vodb_store_fill_synthetic: store is NULL");
+  std::lock_guard<std::mutex> store_lock(s->mu);
   VODB_REQUIRE(n >= 0 && row0 >= 0 && row0 + n <= s->n_rows, "vodb_store_fill_synthetic: rows outside the store");
   DeviceGuard guard(s->device);
   char* dst = reinterpret_cast<char*>(s->data) + (size_t)row0 * s->pitch * dtype_size(s->dtype);
@@ -757,6 +759,7 @@ int vodb_store_fill_synthetic(vodb_store* s, uint64_t seed, int64_t row0, int64_
 
 int vodb_store_read(vodb_store* s, int64_t row0, int64_t n, float* out, int out_on_device, void* stream) {
   VODB_REQUIRE(s != nullptr && out != nullptr, "vodb_store_read: NULL argument");
+  std::lock_guard<std::mutex> store_lock(s->mu);
   VODB_REQUIRE(n >= 0 && row0 >= 0 && row0 + n <= s->n_rows, "vodb_store_read: rows outside the store");
   if (n == 0) return VODB_OK;
   DeviceGuard guard(s->device);
@@ -790,6 +793,7 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
                 float* out_scores, int64_t* out_idx, int out_on_device, void* stream) {
   int rc = check_search_args(s, queries, q_dtype, nq, k, mode, out_scores, out_idx, "vodb_search");
   if (rc != VODB_OK) return rc;
+  std::lock_guard<std::mutex> store_lock(s->mu);
   if (nq == 0) return VODB_OK;
   if (s->n_added <= 0) {
     set_error("vodb_search: the store is empty (faiss health check: 'ERROR: Index is empty')");
@@ -909,11 +913,12 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
                         int mode, int safe, float* out_scores, int64_t* out_idx, int out_on_device, void* stream) {
   int rc = check_search_args(s, queries, q_dtype, nq, k, mode, out_scores, out_idx, "vodb_search_sharded");
   if (rc != VODB_OK) return rc;
+  std::lock_guard<std::mutex> store_lock(s->mu);
   VODB_REQUIRE(x != nullptr && x->connected, "vodb_search_sharded: exchange is NULL or not connected");
   VODB_REQUIRE(x->device == s->device, "vodb_search_sharded: exchange and store live on different devices");
   VODB_REQUIRE(nq >= 1 && (size_t)nq * k <= x->slot, "vodb_search_sharded: nq*k=%lld exceeds the exchange slot (%zu)", (long long)nq * k, x->slot);
   if (is_tensor_mode(mode) && !tensor_path_supported(s)) {
-    set_error("vodb_search_sharded: VODB_MODE_TENSOR* needs a bf16/f16 store");
+    set_error("vodb_search_sharded: VODB_MODE_TENSOR* needs a driver exporting cuTensorMapEncodeTiled");
     return VODB_EUNSUPPORTED;
   }
   DeviceGuard guard(s->device);
@@ -959,6 +964,7 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
 
 int vodb_search_check(vodb_store* s, void* stream) {
   VODB_REQUIRE(s != nullptr, "vodb_search_check: store is NULL");
+  std::lock_guard<std::mutex> store_lock(s->mu);
   Workspace& w = s->ws;
   if (!w.overflow) return 0;
   DeviceGuard guard(s->device);
@@ -971,6 +977,7 @@ int vodb_search_check(vodb_store* s, void* stream) {
 
 int vodb_store_set_profiling(vodb_store* s, int enable) {
   VODB_REQUIRE(s != nullptr, "vodb_store_set_profiling: store is NULL");
+  std::lock_guard<std::mutex> store_lock(s->mu);
   if (!s->prof) s->prof = new ProfileState();
   static_cast<ProfileState*>(s->prof)->reset();
   s->profiling = enable != 0;
@@ -979,6 +986,7 @@ int vodb_store_set_profiling(vodb_store* s, int enable) {
 
 int vodb_store_profile(vodb_store* s, double out[4]) {
   VODB_REQUIRE(s != nullptr && out != nullptr, "vodb_store_profile: NULL argument");
+  std::lock_guard<std::mutex> store_lock(s->mu);
   out[0] = out[1] = out[2] = out[3] = 0.0;
   if (!s->prof) return VODB_OK;
   DeviceGuard guard(s->device);
@@ -1183,6 +1191,7 @@ int vodb_retrieve_sample(vodb_store* s, const void* queries, int q_dtype, int q_
                          int64_t* out_local, void* stream) {
   int rc = check_search_args(s, queries, q_dtype, nq, top_k, mode, out_scores, out_idx, "vodb_retrieve_sample");
   if (rc != VODB_OK) return rc;
+  std::lock_guard<std::mutex> store_lock(s->mu);
   VODB_REQUIRE(top_k <= 8192, "vodb_retrieve_sample: top_k=%d > 8192", top_k);
   VODB_REQUIRE(k_total >= 0 && k_positive >= 0 && k_positive <= k_total,
                "vodb_retrieve_sample: need 0 <= k_positive <= k_total (got %d, %d)", k_positive, k_total);

@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+
+#include <mutex>
 #include <stdint.h>
 
 #include <cstdarg>
@@ -132,6 +134,10 @@ struct Workspace {
 }  // namespace vodb
 
 struct vodb_store {
+  // held by every entry point that touches the store: workspace, staging buffers, tensor-map cache, planes and
+  // statistics are per store, so host threads take turns (the kernels of concurrent callers additionally share the
+  // candidate lists: callers that overlap searches on one store must enqueue them on the same stream)
+  std::mutex mu;
   int device = 0;
   int64_t n_rows = 0;      // capacity
   int64_t n_added = 0;     // rows filled so far
