@@ -430,6 +430,8 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
   // Large batches refresh the thresholds more often (smaller first segment, growth 3 instead of up to 32): the
   // number of survivors per query over the whole scan is ~ k*g*log_{1+g}(n/first), every survivor costs epilogue
   // time, and with thousands of queries that outweighs the fixed cost of a few more (select + launch) pairs.
+  // (scripts/sweep_schedule_large.py, 8192 queries: first 4096 / 16384 rows x growth 2 / 3 / 5 are within +-3% of
+  // each other for k = 100 and k = 1000 — profiles/r01m_schedule_sweep_large.jsonl.)
   const bool large_batch = nq > 256;
   // first segment ("dump": every score stored, then one select). Measured on B200 (scripts/sweep_schedule.py,
   // 64 queries, k=100): 1024..8192 rows and growth 8..32 are within ~1% of each other on a 10M-row shard; on a
@@ -440,6 +442,9 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
   static const char* env_first = std::getenv("VODB_FIRST_ROWS");
   static const char* env_growth = std::getenv("VODB_GROWTH");
   if (env_first && !large_batch) first = round128(std::min<int64_t>(cap / 2, std::max<int64_t>(2LL * k, std::atoll(env_first))));
+  static const char* env_first_large = std::getenv("VODB_FIRST_ROWS_LARGE");
+  static const char* env_growth_large = std::getenv("VODB_GROWTH_LARGE");
+  if (env_first_large && large_batch) first = round128(std::min<int64_t>(cap / 2, std::max<int64_t>(2LL * k, std::atoll(env_first_large))));
   if (first >= n) {
     b.push_back(n);
     return b;
@@ -448,6 +453,7 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
   // growth: expected survivors of a segment = k * seg/before; keep that below cap/8
   double g = std::max(1.0, std::min((double)cap / (8.0 * k), large_batch ? 3.0 : 32.0));
   if (env_growth && !large_batch) g = std::max(1.0, std::min(g, std::atof(env_growth)));
+  if (env_growth_large && large_batch) g = std::max(1.0, std::min((double)cap / (8.0 * k), std::atof(env_growth_large)));
   int64_t cur = first;
   while (cur < n) {
     int64_t seg = round128((int64_t)(g * (double)cur));
