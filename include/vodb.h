@@ -58,7 +58,9 @@ extern "C" {
 /* The tensor modes also serve a float32 store: its rows are then mirrored as three bf16 planes (row = p0 + p1 + p2
  * exactly; 6 more bytes per element, allocated by the first such search, kept in step with later adds) and mode X
  * multiplies the first X planes with X query terms. TENSOR_X3 reproduces the fp32 result within the fp32-exact
- * tolerance (1e-5 relative; measured <= 4e-6) 3-4x faster than VODB_MODE_EXACT. */
+ * tolerance (1e-5 relative; measured <= 4e-6) 3-4x faster than VODB_MODE_EXACT.
+ * Correction terms that are zero for the whole query batch (float32 queries that are exact in the store dtype) are
+ * detected on the device and skipped: TENSOR_X2 / _X3 then cost what TENSOR costs and return the same bits. */
 
 /* error codes */
 #define VODB_OK 0
