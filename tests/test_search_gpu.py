@@ -472,3 +472,23 @@ def test_host_threads_share_a_store():
         th.join()
     assert not errors, errors[0]
     st.close()
+
+
+@pytest.mark.parametrize("dtype,d", [("bfloat16", 1024), ("float16", 2048), ("float32", 512), ("float32", 1024)])
+def test_padded_row_pitch_for_power_of_two_strides(dtype, d):
+    """Rows whose byte length is a multiple of 2 KB are stored with one extra, never scanned 64-element chunk (HBM
+    channel spread, vodb_store_create): every mode, ingest path and read-back must be unaffected."""
+    rng = np.random.default_rng(d)
+    n = 3000
+    xb, xq = int_valued(rng, (n, d)), int_valued(rng, (70, d))
+    st = vod_b200.CorpusStore(n, d, dtype=dtype)
+    st.add(xb[:1000])
+    import torch
+
+    st.add(torch.from_numpy(xb[1000:]).cuda(), row0=1000)              # device ingest
+    assert np.array_equal(st.read(0, n), xb)
+    rs, ri = flat_ip.search(xb, xq, 50)
+    for mode in ("exact", "tensor", "tensor2", "tensor3"):
+        s, i = st.search(xq, 50, mode=mode)
+        assert np.array_equal(i, ri) and np.array_equal(s, rs), mode
+    st.close()

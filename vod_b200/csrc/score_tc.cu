@@ -879,7 +879,7 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.nq = a.nq;
   p.n_ctiles = (int)((a.row_end - a.row_begin + BM - 1) / BM);
   p.n_qtiles = (a.nq + BN - 1) / BN;
-  p.kchunks = s->pitch / KC;
+  p.kchunks = (s->dim + KC - 1) / KC;  // the pitch may carry one more, unscanned chunk (api.cu vodb_store_create)
   p.q_rows_pad = (int)q_rows_pad;
   p.plane_rows = (int)s->n_rows;
   p.cand_s = a.cand_s;
@@ -918,7 +918,7 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.nq = a.nq;
   p.n_ctiles = (int)((a.row_end - a.row_begin + 2 * BM - 1) / (2 * BM));  // 256-row pair tiles
   p.n_qtiles = (a.nq + Cfg::BN - 1) / Cfg::BN;
-  p.kchunks = s->pitch / KC;
+  p.kchunks = (s->dim + KC - 1) / KC;  // the pitch may carry one more, unscanned chunk (api.cu vodb_store_create)
   p.q_rows_pad = (int)q_rows_pad;
   p.plane_rows = 0;
   p.cand_s = a.cand_s;
