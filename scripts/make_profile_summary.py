@@ -98,13 +98,19 @@ for rr in rows[2:]:
     g = lambda k: float(rr[ix[k]])
     A(f"| `{nm}` | {rr[ix['Grid Size']]} x {rr[ix['Block Size']]} | {g('gpu__time_duration.sum')*1e3:.1f} | {g('dram__bytes_read.sum')*1e3:.2f} | {int(g('launch__registers_per_thread'))} | {g('sm__warps_active.avg.pct_of_peak_sustained_active'):.0f} | {g('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'):.0f} | {what.get(base, '')} |")
 A("\nThe fp32-exact CUDA-core scan runs the big segment at 34 TFLOP/s (FMA pipe 49% active, 25% occupancy at 105 registers): compute-bound at 13% of HBM bandwidth, which is why a bf16/fp16 store with 3-term queries on the tensor cores (`tensor3`, same 1e-5 parity) is the recommended exact mode. Everything else is a latency-bound single wave (6-45 us).\n")
-c5 = json.loads((P / 'r01m_c5_n8_probe.json').read_text()); ab = json.loads((P / 'r01m_pitch_pad_ab.json').read_text())
+c5 = json.loads((P / 'r01m_c5_n8_probe.json').read_text())
 A("## BASELINE configs[4] at full size: 50M x 1024 index refresh + fp32-exact search on 8 GPUs (r01m_c5_n8_probe.json, scripts/probe_c5_multi.py)\n")
 A("| step | result |\n|---|---|")
 A(f"| ingest: float32 vectors in pinned host memory (2^18-row batches) -> bf16 row shards, 8 ranks in parallel | {c5['ingest_s']:.2f} s for 50M x 1024 = {c5['ingest_host_GBps_aggregate']:.0f} GB/s of host data in aggregate ({c5['ingest_rows_per_s']/1e6:.0f}M rows/s; one GPU alone: 52 GB/s, so 8 concurrent uploads share the host's memory / PCIe fabric) |")
 A(f"| search, 64 float32 queries, top-100, `tensor3` (fp32-exact on tensor cores), fused peer-memory exchange | {c5['search_tensor3_ms']:.3f} ms per batch = {c5['search_tensor3_qps']:.0f} queries/s, {c5['search_tensor3_GBps_aggregate']/1e3:.1f} TB/s scanned in aggregate; recall vs the CUDA-core fp32 kernel {c5['tensor3_recall_vs_cuda_core_exact']:.4f} |")
 A(f"| same, `tensor` (queries rounded to bf16) | {c5['search_tensor_ms']:.3f} ms = {c5['search_tensor_qps']:.0f} queries/s, {c5['search_tensor_GBps_aggregate']/1e3:.1f} TB/s |")
-A(f"\nThat run still had a dense 2048-byte row stride. Rows whose byte length is a multiple of 2 KB are now stored with one extra, unscanned 64-element chunk (r01m_pitch_pad_ab.json, one shard on one GPU): `tensor` {ab['dense_pitch_1024']['search_tensor_ms']:.2f} -> {ab['padded_pitch_1088']['search_tensor_ms']:.2f} ms ({ab['dense_pitch_1024']['search_tensor_GBps']:.0f} -> {ab['padded_pitch_1088']['search_tensor_GBps']:.0f} GB/s); `tensor3` unchanged ({ab['padded_pitch_1088']['search_tensor3_ms']:.2f} ms: bound by operand bytes in flight, not by the DRAM access pattern).\n")
+ps = [json.loads(l) for l in (P / 'r01m_pitch_sweep.jsonl').read_text().splitlines() if l.startswith('{')]
+A("\nRow length vs scan bandwidth (r01m_pitch_sweep.jsonl, scripts/sweep_pitch.py; bf16, 64 queries, `tensor`): dense pitch / one extra unscanned 64-element chunk per row, GB/s:\n")
+A("| dim | store GB | dense | padded |\n|---|---|---|---|")
+for i in range(0, len(ps) - 1, 2):
+    d0, d1 = ps[i], ps[i + 1]
+    A(f"| {d0['dim']} | {d0['rows']*d0['dim']*2/1e9:.1f} | {d0['GBps']:.0f} | {d1['GBps']:.0f} |")
+A("\nNo penalty for power-of-two row strides (dim 1024 / 2048), and padding never helps: the layout stays dense. (Single runs of the config-4 probe on one shard came out at 1.9 or 2.2-2.3 ms with either layout — run-to-run state of the box, not the stride.)\n")
 sw = [json.loads(l) for l in (P / 'r01k_batch_sweep.jsonl').read_text().splitlines() if l.startswith('{')]
 A("## Roofline curve over the batch size (r01k_batch_sweep.jsonl, scripts/sweep_batch.py; 10M x 768 bf16, top-100, back-to-back searches)\n")
 A("| queries | ms | queries/s | roofline ms = max(bytes / HBM peak, flops / bf16 burst peak) | fraction | bound | segments |\n|---|---|---|---|---|---|---|")

@@ -475,9 +475,9 @@ def test_host_threads_share_a_store():
 
 
 @pytest.mark.parametrize("dtype,d", [("bfloat16", 1024), ("float16", 2048), ("float32", 512), ("float32", 1024)])
-def test_padded_row_pitch_for_power_of_two_strides(dtype, d):
-    """Rows whose byte length is a multiple of 2 KB are stored with one extra, never scanned 64-element chunk (HBM
-    channel spread, vodb_store_create): every mode, ingest path and read-back must be unaffected."""
+def test_power_of_two_row_strides(dtype, d):
+    """Rows of 2 KB / 4 KB (dim 1024 bf16, 2048 fp16, 512 / 1024 fp32): every mode, both ingest paths and the
+    read-back agree with the oracle (the K loop covers ceil(dim / 64) chunks whatever the pitch is)."""
     rng = np.random.default_rng(d)
     n = 3000
     xb, xq = int_valued(rng, (n, d)), int_valued(rng, (70, d))

@@ -677,11 +677,11 @@ int vodb_store_create(vodb_store** out, int device, int64_t n_rows, int dim, int
   s->n_rows = n_rows;
   s->dim = dim;
   s->pitch = (dim + kPitchAlign - 1) / kPitchAlign * kPitchAlign;
-  // A row stride that is a multiple of 2 KB puts the same 128-byte column chunk of consecutive rows — what one TMA box
-  // fetches — on a fraction of the HBM channels. One extra (never scanned) 64-element chunk per row breaks the power
-  // of two; VODB_PITCH_PAD=0 keeps the dense layout (A/B measurements).
+  // Development knob: VODB_PITCH_PAD=2 adds one unscanned 64-element chunk per row. Tested as a remedy for
+  // power-of-two row strides (dim 1024 bf16 = 2 KB): a controlled sweep over row lengths and store sizes showed no
+  // stride penalty and a 0-8% loss from the padding (profiles/r01m_pitch_sweep.jsonl), so the layout stays dense.
   static const char* env_pad = std::getenv("VODB_PITCH_PAD");
-  if (!(env_pad && env_pad[0] == '0') && ((size_t)s->pitch * dtype_size(dtype)) % 2048 == 0) s->pitch += kPitchAlign;
+  if (env_pad && env_pad[0] == '2') s->pitch += kPitchAlign;
   s->dtype = dtype;
   s->row_offset = row_offset;
   cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
