@@ -5,7 +5,7 @@ def bench(name): return json.loads([l for l in (P / name).read_text().splitlines
 out = []; A = out.append
 A("# Round 1 — profile summary (B200, sm_100a)\n")
 A("All numbers from `gpurun` boxes (1x B200 unless noted). Peaks: `MEASURED_PEAKS.json` — HBM 6534.8 GB/s (copy kernel), bf16 1671.7 TFLOP/s burst / 1404.1 sustained (cuBLAS). Workload: BASELINE configs[1], 10M x 768 bf16, exact top-100. Box-to-box variation of the same build is about +-4% (2.19-2.29 ms for the 64-query step).\n")
-A("Files: `r01a_*` first working tcgen05 path; `r01b_*` dump mode + staged survivors; `r01c..g_*` bench lines along the way; `r01h_*` final state of the round (launch list, `ncu --set full` raw pages of `score_tc_kernel<64,1>` and the 2-CTA `score_tc2_kernel`, bench lines of both arms); `r01i_*` multi-GPU bench lines with the flag/fence exchange; `r01j_*` final bench lines of the round (1 GPU both arms, 2/4/8 GPUs with the epoch-tagged LL exchange, 8 GPUs NCCL); `r01l_*`/`r01m_*` bench lines, launch list and `ncu --set full` raw pages of the final build; `r01k_*` BASELINE configs[2] at full size (100M x 768 fp16 over 2/4/8 GPUs, top-1000), `ncu --set full` raw page of the kernels beside the tensor-core scan, latency probe; probes: `r01_schedule_sweep.jsonl`, `r01_query_terms_probe.json`, `r01_configs_3_5_probe.json`, `r01_compute_sanitizer.txt`. Regenerate this file with `python scripts/make_profile_summary.py`.\n")
+A("Files: `r01a_*` first working tcgen05 path; `r01b_*` dump mode + staged survivors; `r01c..g_*` bench lines along the way; `r01h_*` final state of the round (launch list, `ncu --set full` raw pages of `score_tc_kernel<64,1>` and the 2-CTA `score_tc2_kernel`, bench lines of both arms); `r01i_*` multi-GPU bench lines with the flag/fence exchange; `r01j_*` final bench lines of the round (1 GPU both arms, 2/4/8 GPUs with the epoch-tagged LL exchange, 8 GPUs NCCL); `r01l_*`/`r01m_*` bench lines, launch list and `ncu --set full` raw pages of the final tensor-core kernels; `r01n_bench*.json` the last bench lines of the round (after the CUDA-core kernel rework); `r01k_*` BASELINE configs[2] at full size (100M x 768 fp16 over 2/4/8 GPUs, top-1000), `ncu --set full` raw page of the kernels beside the tensor-core scan, latency probe; probes: `r01_schedule_sweep.jsonl`, `r01_query_terms_probe.json`, `r01_configs_3_5_probe.json`, `r01_compute_sanitizer.txt`. Regenerate this file with `python scripts/make_profile_summary.py`.\n")
 d = bench("r01m_bench.json"); f = bench("r01h_bench.json")
 A("## Headline (r01m_bench.json = final build of the round, same gpurun call as the r01m ncu captures below; r01h_bench.json = an earlier build on another box)\n")
 A("| quantity | r01m | r01h |\n|---|---|---|")
@@ -97,7 +97,7 @@ for rr in rows[2:]:
     seen[key] = 1
     g = lambda k: float(rr[ix[k]])
     A(f"| `{nm}` | {rr[ix['Grid Size']]} x {rr[ix['Block Size']]} | {g('gpu__time_duration.sum')*1e3:.1f} | {g('dram__bytes_read.sum')*1e3:.2f} | {int(g('launch__registers_per_thread'))} | {g('sm__warps_active.avg.pct_of_peak_sustained_active'):.0f} | {g('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'):.0f} | {what.get(base, '')} |")
-A("\nThe fp32-exact CUDA-core scan runs the big segment at 34 TFLOP/s (FMA pipe 49% active, 25% occupancy at 105 registers): compute-bound at 13% of HBM bandwidth, which is why a bf16/fp16 store with 3-term queries on the tensor cores (`tensor3`, same 1e-5 parity) is the recommended exact mode. Everything else is a latency-bound single wave (6-45 us).\n")
+A("\nThe fp32-exact CUDA-core scan of this capture (first version of the kernel) runs the big segment at 34 TFLOP/s (FMA pipe 49% active, LSU pipe 69% busy with shared-memory wavefronts, 4-way conflicts on the transposing stores); the current kernel (8x8 thread tile, swizzled stores) is 18% faster at 64 queries. Still compute-bound at ~15% of HBM bandwidth, which is why a bf16/fp16 store with 3-term queries on the tensor cores (`tensor3`, same 1e-5 parity) is the recommended exact mode. Everything else is a latency-bound single wave (6-45 us).\n")
 c5 = json.loads((P / 'r01m_c5_n8_probe.json').read_text())
 A("## BASELINE configs[4] at full size: 50M x 1024 index refresh + fp32-exact search on 8 GPUs (r01m_c5_n8_probe.json, scripts/probe_c5_multi.py)\n")
 A("| step | result |\n|---|---|")
