@@ -1,7 +1,6 @@
 """Why is an isolated 64-query search slower than one of a back-to-back stream? Per-call CUDA-event time and the
 library's per-kernel event sums (vodb_store_set_profiling) under different submission patterns. Run on the GPU box."""
 import json
-import sys
 import time
 
 import torch

@@ -1,4 +1,4 @@
-import sys, time, json
+import sys, json
 sys.path.insert(0, '.')
 import numpy as np, torch
 import vod_b200

@@ -2,7 +2,6 @@
 import ctypes
 
 import numpy as np
-import pytest
 
 
 def test_philox_known_answers(twin):

@@ -9,7 +9,6 @@ score -inf / index -1 by `RetrievalBatch.stack_samples`.
 from __future__ import annotations
 
 import collections
-import typing as typ
 
 import numpy as np
 
