@@ -28,39 +28,37 @@ def _array_repr(x: typ.Any) -> str:
 
 
 class RetrievalData:
-    """Model search results (retrieval.py:18-133)."""
+    """Model search results (retrieval.py:18-133): `scores`, `indices`, optional `labels`, free-form `meta`."""
 
     __slots__ = ("scores", "indices", "labels", "allow_unsafe", "meta")
     _expected_dim: int = -1
 
     def __init__(self, scores, indices, labels=None, meta=None, allow_unsafe: bool = False):
-        dim = len(indices.shape)
-        if not allow_unsafe and scores.shape[:dim] != indices.shape[:dim]:
-            raise ValueError(
-                "The shapes of `scores` and `indices` must match up to the dimension of `indices`, "
-                f"but got {_array_repr(scores)} and {_array_repr(indices)}"
-            )
-        if labels is not None and (scores.shape[:dim] != labels.shape[:dim]):
+        lead = len(indices.shape)  # scores may carry extra trailing dims; the leading ones must agree
+        if not allow_unsafe and scores.shape[:lead] != indices.shape[:lead]:
+            raise ValueError("The shapes of `scores` and `indices` must match up to the dimension of `indices`, "
+                             f"but got {_array_repr(scores)} and {_array_repr(indices)}")
+        if labels is not None and scores.shape[:lead] != labels.shape[:lead]:
             raise ValueError("The shapes of `scores` and `labels` must match up to the dimension of `indices`, ")
         if len(scores.shape) != self._expected_dim:
-            raise ValueError(
-                f"Scores must be {self._expected_dim}D, but got {_array_repr(scores)} and {_array_repr(indices)}"
-            )
-        self.allow_unsafe = allow_unsafe
-        self.scores = scores
-        self.indices = indices
-        self.labels = labels
+            raise ValueError(f"Scores must be {self._expected_dim}D, but got {_array_repr(scores)} and {_array_repr(indices)}")
+        self.scores, self.indices, self.labels = scores, indices, labels
         self.meta = meta or {}
+        self.allow_unsafe = allow_unsafe
+
+    def _arrays(self) -> tuple:
+        return self.scores, self.indices, self.labels
+
+    def _derive(self, cls: type, fn: typ.Callable[[typ.Any], typ.Any], **kw: typ.Any) -> "RetrievalData":
+        """New container of type `cls` with `fn` applied to scores, indices and (if present) labels."""
+        s, i, lab = self._arrays()
+        return cls(fn(s), fn(i), None if lab is None else fn(lab), **kw)
 
     @classmethod
     def cast(cls, scores, indices, labels=None, meta=None, allow_unsafe: bool = False):
-        return cls(
-            scores=_cast_to_numpy(scores),
-            indices=_cast_to_numpy(indices),
-            labels=_cast_to_numpy(labels) if labels is not None else None,
-            meta=meta,
-            allow_unsafe=allow_unsafe,
-        )
+        """Build from lists / numpy arrays / torch tensors (converted to numpy)."""
+        as_np = [None if x is None else _cast_to_numpy(x) for x in (scores, indices, labels)]
+        return cls(*as_np, meta=meta, allow_unsafe=allow_unsafe)
 
     def __len__(self) -> int:
         return len(self.scores)
@@ -79,75 +77,61 @@ class RetrievalData:
         return bool(np.all(self.scores == other.scores) and np.all(self.indices == other.indices))
 
     def to_dict(self) -> dict[str, typ.Any]:
-        return {
-            "scores": self.scores.tolist(),
-            "indices": self.indices.tolist(),
-            "labels": self.labels.tolist() if self.labels is not None else None,
-        }
+        return {name: None if arr is None else arr.tolist()
+                for name, arr in zip(("scores", "indices", "labels"), self._arrays())}
 
 
 class RetrievalTuple(RetrievalData):
     _expected_dim = 0
 
 
-class RetrievalSample(RetrievalData):
-    _expected_dim = 1
+class _Indexable(RetrievalData):
+    """Row access shared by samples (rows are tuples) and batches (rows are samples)."""
 
-    def __getitem__(self, item: int) -> RetrievalTuple:
-        return RetrievalTuple(
-            scores=self.scores[item],
-            indices=self.indices[item],
-            labels=self.labels[item] if self.labels is not None else None,
-        )
+    _row_cls: type = RetrievalData
+
+    def __getitem__(self, item: int):
+        return self._derive(self._row_cls, lambda arr: arr[item])
 
     def __iter__(self):
-        for i in range(len(self)):
-            yield self[i]
+        return (self[i] for i in range(len(self)))
+
+
+class RetrievalSample(_Indexable):
+    _expected_dim = 1
+    _row_cls = RetrievalTuple
 
     def __add__(self, other: "RetrievalSample") -> "RetrievalBatch":
         return stack_samples([self, other])
 
 
-class RetrievalBatch(RetrievalData):
+class RetrievalBatch(_Indexable):
     """A batch of search results: scores f32[B,K], indices i64[B,K] (retrieval.py:179-249)."""
 
     _expected_dim = 2
-
-    def __getitem__(self, item: int) -> RetrievalSample:
-        return RetrievalSample(
-            scores=self.scores[item],
-            indices=self.indices[item],
-            labels=self.labels[item] if self.labels is not None else None,
-        )
-
-    def __iter__(self):
-        for i in range(len(self)):
-            yield self[i]
+    _row_cls = RetrievalSample
 
     def __add__(self, other: "RetrievalBatch") -> "RetrievalBatch":
-        return RetrievalBatch(
-            scores=np.concatenate([self.scores, other.scores]),
-            indices=np.concatenate([self.indices, other.indices]),
-            labels=_merge_labels(self.labels, other.labels),
-        )
+        """Concatenate along the batch axis; a side without labels contributes -1."""
+        lab_a, lab_b = self.labels, other.labels
+        if (lab_a is None) != (lab_b is None):
+            lab_a = np.full_like(lab_b, -1) if lab_a is None else lab_a
+            lab_b = np.full_like(lab_a, -1) if lab_b is None else lab_b
+        return RetrievalBatch(np.concatenate([self.scores, other.scores]), np.concatenate([self.indices, other.indices]),
+                              None if lab_a is None else np.concatenate([lab_a, lab_b]))
 
     def sorted(self) -> "RetrievalBatch":
-        """Sort by score, descending (retrieval.py:211-220)."""
-        sort_ids = np.flip(np.argsort(self.scores, axis=-1), axis=-1)
-        return RetrievalBatch(
-            scores=np.take_along_axis(self.scores, sort_ids, axis=-1),
-            indices=np.take_along_axis(self.indices, sort_ids, axis=-1),
-            labels=np.take_along_axis(self.labels, sort_ids, axis=-1) if self.labels is not None else None,
-            meta=copy.copy(self.meta),
-        )
+        """Sort every row by score, descending (retrieval.py:211-220)."""
+        order = np.flip(np.argsort(self.scores, axis=-1), axis=-1)
+        return self._derive(RetrievalBatch, lambda arr: np.take_along_axis(arr, order, axis=-1), meta=copy.copy(self.meta))
 
     def __mul__(self, value: float) -> "RetrievalBatch":
         if not isinstance(value, Number):
             raise TypeError(f"Expected a number, but got `{type(value)}`")
-        with warnings.catch_warnings():
+        with warnings.catch_warnings():  # inf * 0 in padded slots is expected
             warnings.filterwarnings("ignore", category=RuntimeWarning)
-            return RetrievalBatch(scores=self.scores * value, indices=self.indices, labels=self.labels,
-                                  meta=copy.copy(self.meta))
+            scaled = self.scores * value
+        return RetrievalBatch(scaled, self.indices, self.labels, meta=copy.copy(self.meta))
 
     @classmethod
     def stack_samples(cls, samples: typ.Iterable[RetrievalSample]) -> "RetrievalBatch":
@@ -155,15 +139,16 @@ class RetrievalBatch(RetrievalData):
 
     @classmethod
     def concatenate_batches(cls, batches: typ.Iterable["RetrievalBatch"]) -> "RetrievalBatch":
-        output = None
-        for batch in batches:
-            output = batch if output is None else output + batch
-        if output is None:
+        batches = list(batches)
+        if not batches:
             raise ValueError("Cannot concatenate an empty list of batches")
-        return output
+        total = batches[0]
+        for nxt in batches[1:]:
+            total = total + nxt
+        return total
 
 
-def _stack_1d(arrays: list[np.ndarray], fill_value: typ.Any) -> np.ndarray:
+def _pad_rows(arrays: list[np.ndarray], fill_value: typ.Any) -> np.ndarray:
     width = max(len(a) for a in arrays)
     out = np.full((len(arrays), width), fill_value, dtype=arrays[0].dtype)
     for j, a in enumerate(arrays):
@@ -172,21 +157,8 @@ def _stack_1d(arrays: list[np.ndarray], fill_value: typ.Any) -> np.ndarray:
 
 
 def stack_samples(samples: typ.Iterable[RetrievalSample]) -> RetrievalBatch:
-    """Stack ragged samples, padding with score -inf / index -1 / label -1 (retrieval.py:276-287)."""
+    """Stack ragged samples into a batch, padding with score -inf / index -1 / label -1 (retrieval.py:276-287)."""
     samples = list(samples)
-    labels = [s.labels for s in samples]
-    return RetrievalBatch(
-        scores=_stack_1d([s.scores for s in samples], -math.inf),
-        indices=_stack_1d([s.indices for s in samples], -1),
-        labels=None if any(lbl is None for lbl in labels) else _stack_1d(labels, -1),
-    )
-
-
-def _merge_labels(a, b):
-    if a is None and b is None:
-        return None
-    if a is None:
-        a = np.full_like(b, fill_value=-1)
-    if b is None:
-        b = np.full_like(a, fill_value=-1)
-    return np.concatenate([a, b])
+    with_labels = all(s.labels is not None for s in samples)
+    return RetrievalBatch(_pad_rows([s.scores for s in samples], -math.inf), _pad_rows([s.indices for s in samples], -1),
+                          _pad_rows([s.labels for s in samples], -1) if with_labels else None)

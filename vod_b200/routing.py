@@ -52,31 +52,26 @@ class ShardedSearchClient(SearchClient):
             raise ValueError("Must specify `shard`")
         if set(shard) > set(self.shards.keys()):
             raise ValueError(f"Invalid shard names {shard}. Valid names are {self.shards.keys()}")
-        queries, lookup = _scatter_queries(text=text, shard=shard, vector=vector, subset_ids=subset_ids, ids=ids)
-        results_by_shard = {}
-        for shard_name, query in queries.items():
-            result = self.shards[shard_name].search(
-                text=query["text"], ids=query["ids"], subset_ids=query["subset_ids"],
-                vector=np.stack(query["vector"]) if vector is not None else None, top_k=top_k)
-            result.indices += self.offsets[shard_name]  # in place, sharded_search.py:103
-            results_by_shard[shard_name] = result
-        gathered = [results_by_shard[name][j] for name, j in lookup]
-        cls = type(next(iter(results_by_shard.values()))) if results_by_shard else RetrievalBatch
-        return cls.stack_samples(gathered)
+        rows_of = _rows_by_shard(shard)
+        # one sub-batch per corpus, rows in input order; absent optional fields stay absent ([] like the reference)
+        where: dict[int, tuple[ShardName, int]] = {}
+        results: dict[ShardName, RetrievalBatch] = {}
+        for name, rows in rows_of.items():
+            pick = lambda seq: [] if seq is None else [seq[i] for i in rows]  # noqa: E731
+            result = self._shards[name].search(text=pick(text), ids=pick(ids), subset_ids=pick(subset_ids),
+                                               vector=None if vector is None else np.stack([vector[i] for i in rows]),
+                                               top_k=top_k)
+            result.indices += self._offsets[name]  # in place, -1 padding included (sharded_search.py:103)
+            results[name] = result
+            where.update({row: (name, local) for local, row in enumerate(rows)})
+        ordered = [results[name][local] for name, local in (where[i] for i in range(len(shard)))]
+        cls = type(next(iter(results.values()))) if results else RetrievalBatch
+        return cls.stack_samples(ordered)
 
 
-def _scatter_queries(text, shard, vector=None, subset_ids=None, ids=None):
-    """sharded_search.py:176-194: group the rows by shard name, remember (shard, local row) per input row."""
-    shards: dict = collections.defaultdict(lambda: collections.defaultdict(list))
-    lookup = []
-    for i, shard_name in enumerate(shard):
-        shards[shard_name]["text"].append(text[i])
-        shards[shard_name]["local_rank"].append(i)
-        lookup.append((shard_name, len(shards[shard_name]["text"]) - 1))
-        if subset_ids is not None:
-            shards[shard_name]["subset_ids"].append(subset_ids[i])
-        if ids is not None:
-            shards[shard_name]["ids"].append(ids[i])
-        if vector is not None:
-            shards[shard_name]["vector"].append(vector[i])
-    return dict(shards), lookup
+def _rows_by_shard(shard: list[ShardName]) -> dict[ShardName, list[int]]:
+    """Input rows of every corpus, in order of first appearance (the scatter step of sharded_search.py:176-194)."""
+    groups: dict[ShardName, list[int]] = collections.OrderedDict()
+    for row, name in enumerate(shard):
+        groups.setdefault(name, []).append(row)
+    return groups
