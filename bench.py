@@ -425,7 +425,10 @@ def main():
                        "chain_ms_p50": times[len(times) // 2], "chain_ms_p90": times[(len(times) * 9) // 10],
                        "sampler_kernel_us_p50": samp[len(samp) // 2],
                        "sample_search_results_host_call_ms_p50": host_call[len(host_call) // 2]}
-            config4["dataloader_workers"] = worker_clients_section(corpus.store)
+            try:
+                config4["dataloader_workers"] = worker_clients_section(corpus.store)
+            except Exception as exc:  # worker processes are a side measurement: never lose the chain numbers over them
+                config4["dataloader_workers"] = {"error": f"{type(exc).__name__}: {exc}"}
         except Exception as exc:
             config4 = {"error": f"{type(exc).__name__}: {exc}"}
 
