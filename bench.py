@@ -178,8 +178,15 @@ def worker_clients_section(store, n_workers: int = 8, n_batches: int = 12):
                 arg = pickle.dumps((server.address, server.authkey, n_batches, w)).hex()
                 procs.append(subprocess.Popen([sys.executable, "-c", _WORKER_CODE, arg], stdin=subprocess.PIPE,
                                               stdout=subprocess.PIPE, text=True, cwd=root))
+            def line_from(p, timeout_s):  # a stuck worker must not hang the bench
+                import select
+
+                if not select.select([p.stdout], [], [], timeout_s)[0]:
+                    raise TimeoutError("search worker did not answer")
+                return p.stdout.readline()
+
             for p in procs:
-                if p.stdout.readline().strip() != "ready":
+                if line_from(p, 120).strip() != "ready":
                     raise RuntimeError("search worker failed to start")
             scans0 = server.coalescer.n_scans if server.coalescer else 0
             t0 = time.perf_counter()
@@ -187,7 +194,7 @@ def worker_clients_section(store, n_workers: int = 8, n_batches: int = 12):
                 p.stdin.write("go\n")
                 p.stdin.flush()
             for p in procs:
-                float(p.stdout.readline())
+                float(line_from(p, 120))
             dt = time.perf_counter() - t0
             out[label] = n_workers * n_batches * 32 / dt
             if server.coalescer:
