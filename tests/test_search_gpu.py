@@ -492,3 +492,21 @@ def test_power_of_two_row_strides(dtype, d):
         s, i = st.search(xq, 50, mode=mode)
         assert np.array_equal(i, ri) and np.array_equal(s, rs), mode
     st.close()
+
+
+def test_client_accepts_cuda_tensors():
+    """`search(vector=<CUDA tensor>)`: encoder outputs go to the search without a host round trip of the queries;
+    results equal the numpy path (bf16 tensor, float32 tensor, and a CPU tensor)."""
+    import torch
+
+    rng = np.random.default_rng(41)
+    xb, xq = int_valued(rng, (20_000, 128)), int_valued(rng, (33, 128))
+    with vod_b200.B200SearchMaster(xb, dtype="bfloat16") as master:
+        client = master.get_client()
+        ref = client.search(vector=xq, top_k=40)
+        for t in (torch.from_numpy(xq).cuda(), torch.from_numpy(xq).cuda().to(torch.bfloat16), torch.from_numpy(xq)):
+            out = client.search(vector=t, top_k=40)
+            assert np.array_equal(out.indices, ref.indices) and np.array_equal(out.scores, ref.scores)
+            assert out.scores.flags.writeable and isinstance(out.scores, np.ndarray)
+        with pytest.raises(ValueError):
+            client.search(vector=torch.zeros(128).cuda(), top_k=3)

@@ -371,16 +371,36 @@ class B200SearchClient(SearchClient):
         if m is not None:
             if m.store is None:
                 raise _lib.VodbError("the master has not been entered (`with master as m:`)")
-            scores, indices = m.store.search(vector, top_k, mode=self.mode or m.mode)
+            mode = self.mode or m.mode
+            if hasattr(vector, "is_cuda"):  # torch tensor: queries straight from the encoder, no host round trip
+                if vector.is_cuda and isinstance(m.store, CorpusStore) and vector.device.index == m.store.device:
+                    scores, indices = _search_cuda_tensor(m.store, vector, top_k, mode)
+                else:
+                    scores, indices = m.store.search(vector.detach().float().cpu().numpy(), top_k, mode=mode)
+            else:
+                scores, indices = m.store.search(vector, top_k, mode=mode)
         elif self.pid == os.getpid():
             raise _lib.VodbError("the B200SearchMaster of this client is not active (`with master as m:`)")
         else:
-            q = np.ascontiguousarray(vector)
+            q = np.ascontiguousarray(vector.detach().float().cpu().numpy() if hasattr(vector, "is_cuda") else vector)
             if q.ndim != 2:
                 raise ValueError(f"Expected 2D array, got {q.ndim}D array")  # server.py:82-83
             scores, indices = self._remote_search().search(q, top_k, self.mode)
         return _retrieval_batch_cls().cast(indices=indices, scores=scores, labels=None,
                                            meta={"time": time.time() - start_time})
+
+
+def _search_cuda_tensor(store: CorpusStore, vector: typ.Any, top_k: int, mode: str | int | None):
+    """CUDA tensor in (float32 / bfloat16 / float16, on the store's device), numpy results out; a list overflow on
+    the fast schedule (reported by the device flag) falls back to the synchronous entry point."""
+    if vector.dim() != 2:
+        raise ValueError(f"Expected 2D array, got {vector.dim()}D array")  # server.py:82-83
+    q = vector.detach().contiguous()
+    scores, indices = store.search_device(q, top_k, mode=mode)
+    host = scores.cpu().numpy(), indices.cpu().numpy()
+    if store.check_async():
+        return store.search(q.float().cpu().numpy(), top_k, mode=mode)
+    return host
 
 
 class B200SearchMaster:
