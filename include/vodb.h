@@ -190,6 +190,12 @@ int vodb_merge_results(int device, int n_engines, const void* const* scores, con
                        int label_engine, int out_width, void* out_scores, int64_t* out_indices,
                        int64_t* out_labels, void* out_raw, int* out_counts, int on_device, void* stream);
 
+/* The scan schedule vodb_search would use for a shard of n_rows rows (host logic only, no GPU needed): list capacity
+ * per query in *out_cap and the segment boundaries b_0 = 0 < b_1 < ... = n_rows in out_bounds (at most max_bounds
+ * written). Segment 0 is scored in dump mode, every later one against the threshold published by the select after
+ * its predecessor; `safe` is the overflow-proof schedule used for the re-run. Returns the number of boundaries. */
+int vodb_plan_scan(int64_t n_rows, int nq, int k, int safe, int* out_cap, int64_t* out_bounds, int max_bounds);
+
 /* ---- labeled priority sampling ------------------------------------------ */
 
 /* Per row b of scores[B,K]: split entries by labels[b,:] > 0, priority-sample

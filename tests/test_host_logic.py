@@ -107,3 +107,43 @@ def test_build_rejects_non_flat_and_matrix_vectors():
         vod_b200.build_b200_index(np.zeros((4, 8), np.float32), factory_string="IVF16,Flat")
     with pytest.raises(ValueError):
         vod_b200.build_b200_index(np.zeros((4, 8, 2), np.float32))
+
+
+def _plan(n_rows, nq, k, safe=False):
+    import ctypes
+
+    from vod_b200 import _lib
+
+    lib = _lib.load()
+    cap = ctypes.c_int()
+    bounds = (ctypes.c_int64 * 65536)()
+    n = lib.vodb_plan_scan(n_rows, nq, k, int(safe), ctypes.byref(cap), bounds, 65536)
+    assert 2 <= n <= 65536, _lib.last_error()
+    return cap.value, list(bounds[:n])
+
+
+@pytest.mark.parametrize("n_rows", [1, 100, 4096, 5000, 1_250_000, 10_000_000, 100_000_001])
+@pytest.mark.parametrize("nq,k", [(1, 1), (64, 100), (64, 1000), (300, 7), (8192, 100), (8192, 2048)])
+def test_scan_schedule_invariants(n_rows, nq, k):
+    """The C++ planner behind vodb_search (no GPU involved): segments tile the shard, start on 128-row tile
+    boundaries, the dump segment fits a list, and the safe schedule can never overflow one."""
+    for safe in (False, True):
+        cap, b = _plan(n_rows, nq, k, safe)
+        assert cap >= 4 * k and cap & (cap - 1) == 0 and nq * cap * 8 <= max(4 << 30, nq * 8192 * 8)
+        assert b[0] == 0 and b[-1] == n_rows and all(x < y for x, y in zip(b, b[1:]))
+        assert all(x % 128 == 0 for x in b[:-1])
+        assert b[1] - b[0] <= cap                      # dump mode: slot = row - row_begin
+        if safe:
+            assert all(y - x <= cap - k for x, y in zip(b, b[1:]))   # k kept + every row of a segment still fits
+    _, small = _plan(n_rows, 64, k)
+    _, large = _plan(n_rows, 8192, k)
+    assert len(large) >= len(small)                    # large batches refresh the thresholds more often
+
+
+def test_scan_schedule_headline_shapes():
+    cap, b = _plan(10_000_000, 64, 100)
+    assert cap == 16384 and len(b) - 1 == 4 and b[1] == 4096            # BASELINE configs[1], 64 queries
+    cap, b = _plan(10_000_000, 8192, 100)
+    assert len(b) - 1 == 7
+    cap, b = _plan(12_500_000, 64, 1000)
+    assert cap == 65536

@@ -1018,6 +1018,17 @@ int vodb_store_profile(vodb_store* s, double out[4]) {
   return VODB_OK;
 }
 
+int vodb_plan_scan(int64_t n_rows, int nq, int k, int safe, int* out_cap, int64_t* out_bounds, int max_bounds) {
+  VODB_REQUIRE(n_rows >= 1 && nq >= 1 && k >= 1 && k <= VODB_MAX_K, "vodb_plan_scan: bad sizes");
+  VODB_REQUIRE(out_cap != nullptr && out_bounds != nullptr && max_bounds >= 2, "vodb_plan_scan: bad output arguments");
+  const int cap = choose_cap(nq, k);
+  const std::vector<int64_t> b = plan_segments(n_rows, cap, k, nq, safe != 0);
+  *out_cap = cap;
+  const int n = (int)std::min<size_t>(b.size(), (size_t)max_bounds);
+  std::memcpy(out_bounds, b.data(), (size_t)n * sizeof(int64_t));
+  return (int)b.size();
+}
+
 int vodb_search_stats(const vodb_store* s, int64_t out[8]) {
   VODB_REQUIRE(s != nullptr && out != nullptr, "vodb_search_stats: NULL argument");
   std::memcpy(out, s->stats, sizeof(s->stats));
