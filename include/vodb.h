@@ -32,7 +32,9 @@
  *     each owning one store with its `row_offset`; per-shard results are
  *     exchanged by the host code (NCCL all-gather) and reduced by vodb_merge_topk;
  *   - every call on a store takes the store's mutex, so host threads take turns; searches that are enqueued
- *     asynchronously (out_on_device) share the store's candidate lists and must go to the same stream.
+ *     asynchronously (out_on_device) share the store's candidate lists: calls on one stream are ordered by the
+ *     stream, and a call that arrives on a different stream than its predecessor first waits for the device to
+ *     drain (correct on any mix of streams; keep one stream per store for full asynchrony).
  */
 #ifndef VODB_H_
 #define VODB_H_
@@ -92,7 +94,8 @@ int vodb_store_create(vodb_store** out, int device, int64_t n_rows, int dim, int
 void vodb_store_destroy(vodb_store* s);
 
 /* Copy rows [row0, row0+n) into the store, converting src_dtype -> store dtype
- * (round-to-nearest-even) on the device. `rows` is row-major [n, dim]. */
+ * (round-to-nearest-even) on the device. `rows` is row-major [n, dim]. Rows are appended or overwritten:
+ * row0 <= vodb_store_ntotal() (faiss `index.add` appends); a block that would leave a gap is VODB_EINVAL. */
 int vodb_store_add(vodb_store* s, const void* rows, int src_dtype, int src_on_device,
                    int64_t row0, int64_t n, void* stream);
 
@@ -212,6 +215,17 @@ int vodb_sample(int device, const float* scores, const uint8_t* labels, const fl
                 int K, int k_positive, int k_total, int normalized, float temperature,
                 int max_support, int quirks, uint64_t seed, uint64_t offset, int64_t* out_ids,
                 float* out_logw, uint8_t* out_labels, float* out_lse, int on_device, void* stream);
+
+/* `sample_search_results` (src/vod_dataloaders/core/sample.py:22-84) on host arrays in one call: vodb_sample with
+ * normalized=1 over scores[B,K] / labels[B,K] (uint8, NULL = no positives), then the gathers at the picks
+ * (sample.py:57-64: out_idx = indices[b, local], out_scores = scores[b, local]; an unused slot, local = -1, reads the
+ * LAST column like numpy's take_along_axis) and out_msid[b] = max_sampling_id (sample.py:66-71), all on the device.
+ * out_local (optional) receives the sampled positions so that the caller can gather further per-engine raw scores.
+ * Outputs equal vodb_retrieve_sample's for the same lists, bit for bit. 1 <= K <= 8192. */
+int vodb_sample_results(int device, const float* scores, const int64_t* indices, const uint8_t* labels,
+                        const float* noise /* as vodb_sample; NULL = Philox */, int B, int K, int k_positive, int k_total, float temperature, int max_support, int quirks,
+                        uint64_t seed, uint64_t offset, int64_t* out_idx, float* out_scores, float* out_logw,
+                        uint8_t* out_labels, float* out_lse, float* out_msid, int64_t* out_local, void* stream);
 
 /* ---- retrieve -> sample chain --------------------------------------------- */
 

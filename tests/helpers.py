@@ -65,3 +65,33 @@ def round_to(x: np.ndarray, dtype: str) -> np.ndarray:
     if dtype in ("float16", "f16"):
         return t.to(torch.float16).to(torch.float32).numpy()
     return x.astype(np.float32)
+
+
+def results_cases(npz):
+    """Cases of tests/golden/sample_results_ref.npz (outputs of the reference's own sample_search_results)."""
+    for cid, total, k_pos, temperature, support, has_labels in npz["meta"]:
+        p = f"c{int(cid):03d}_"
+        yield dict(cid=int(cid), total=int(total), k_positive=int(k_pos), temperature=float(temperature),
+                   support=None if support < 0 else int(support),
+                   scores=npz[p + "scores"], indices=npz[p + "indices"], sparse=npz[p + "sparse"], noise=npz[p + "noise"],
+                   labels=npz[p + "labels"] if has_labels else None,
+                   o_indices=npz[p + "o_indices"], o_scores=npz[p + "o_scores"], o_labels=npz[p + "o_labels"],
+                   o_logw=npz[p + "o_logw"], o_msid=npz[p + "o_msid"], o_lse_pos=npz[p + "o_lse_pos"],
+                   o_lse_neg=npz[p + "o_lse_neg"], o_raw_dense=npz[p + "o_raw_dense"], o_raw_sparse=npz[p + "o_raw_sparse"])
+
+
+def assert_results_match_reference(case, indices, scores, labels, logw, msid, lse_pos, lse_neg, raw):
+    """One PrioritySampledSections against the reference function's output for the same inputs and noise: picks,
+    gathered values, labels and max_sampling_id exactly; log-weights / normalisers within the fastmath tolerance."""
+    cid = case["cid"]
+    assert not np.isnan(case["o_logw"]).any(), "golden case hit the numba fastmath NaN quirk; regenerate without it"
+    assert np.array_equal(indices, case["o_indices"]), cid
+    assert np.array_equal(scores.view(np.uint32), case["o_scores"].view(np.uint32)), cid
+    assert np.array_equal(labels, case["o_labels"]), cid
+    assert np.array_equal(msid, case["o_msid"]), cid
+    assert np.array_equal(np.isfinite(logw), np.isfinite(case["o_logw"])), cid
+    fin = np.isfinite(logw)
+    assert np.abs(logw[fin] - case["o_logw"][fin]).max(initial=0.0) <= 4e-5, cid
+    assert np.allclose(lse_pos, case["o_lse_pos"], atol=1e-5) and np.allclose(lse_neg, case["o_lse_neg"], atol=1e-5), cid
+    for name in ("dense", "sparse"):
+        assert np.array_equal(raw[name].view(np.uint32), case["o_raw_" + name].view(np.uint32)), (cid, name)

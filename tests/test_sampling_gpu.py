@@ -243,3 +243,24 @@ def test_chain_with_fewer_rows_than_picks_wraps_like_numpy():
     with pytest.raises(ValueError):
         vod_b200.DenseRetrievalSampler(st, top_k=8, total=4, max_pos_sections=5)(xq)
     st.close()
+
+
+def test_sample_search_results_matches_the_reference_function():
+    """vod_b200.sample_search_results (sampler kernel + gather kernel, one C call) against the outputs of the
+    reference's own sample_search_results on the same inputs and the same Exp(1) noise (50 golden cases)."""
+    import pathlib
+
+    from tests.helpers import assert_results_match_reference, results_cases
+
+    npz = np.load(pathlib.Path(__file__).parent / "golden" / "sample_results_ref.npz")
+    n = 0
+    for case in results_cases(npz):
+        batch = vod_b200.RetrievalBatch(scores=case["scores"], indices=case["indices"], labels=case["labels"])
+        out = vod_b200.sample_search_results(search_results=batch, raw_scores={"dense": case["scores"], "sparse": case["sparse"]},
+                                             total=case["total"], max_pos_sections=case["k_positive"],
+                                             temperature=case["temperature"], max_support_size=case["support"],
+                                             noise=case["noise"])
+        assert_results_match_reference(case, out.batch.indices, out.batch.scores, out.batch.labels, out.log_weights,
+                                       out.max_sampling_id, out.lse_pos, out.lse_neg, out.raw_scores)
+        n += 1
+    assert n == 50

@@ -135,3 +135,29 @@ def test_labeled_priority_sampling_unbiased(twin, seed, label_thres, n_trials=30
         assert np.isclose(mu_a, np.mean(mu_a_hats), atol=10.0 / np.sqrt(n_trials * min(k_positive, np.sum(labels == 1))))
     if mu_b is not None:
         assert np.isclose(mu_b, np.mean(mu_b_hats), atol=10.0 / np.sqrt(n_trials * min(k_total - k_positive, np.sum(labels == 0))))
+
+
+def test_twin_plus_numpy_glue_reproduces_the_reference_sample_search_results(twin):
+    """The whole reference function (sample.py:22-84), not just its numba core: 50 cases generated by
+    tests/golden/make_golden_results.py from the reference's own sample_search_results with recorded noise."""
+    import pathlib
+
+    from tests.helpers import assert_results_match_reference, results_cases
+
+    npz = np.load(pathlib.Path(__file__).parent / "golden" / "sample_results_ref.npz")
+    n = 0
+    for case in results_cases(npz):
+        lab = None if case["labels"] is None else case["labels"] > 0
+        ms = case["support"]
+        local, logw, olab, lse = twin.sample(case["scores"], lab, k_positive=case["k_positive"], k_total=case["total"],
+                                             temperature=case["temperature"],
+                                             max_support=-1 if ms is None else max(ms, case["total"]), noise=case["noise"])
+        take = lambda a: np.take_along_axis(a, local, axis=-1)  # noqa: E731
+        picked = take(case["scores"])
+        neg_ref = np.ones_like(case["scores"], bool) if lab is None else ~lab
+        floor = np.amin(np.where(~olab & np.isfinite(picked), picked, np.inf), axis=-1, keepdims=True)
+        msid = (neg_ref & np.isfinite(case["scores"]) & (case["scores"] >= floor)).astype(np.float32).sum(-1)
+        assert_results_match_reference(case, take(case["indices"]), picked, olab, logw, msid, lse[:, 0], lse[:, 1],
+                                       {"dense": picked, "sparse": take(case["sparse"])})
+        n += 1
+    assert n == 50

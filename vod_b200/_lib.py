@@ -59,6 +59,9 @@ _SIGNATURES = {
                                       _c.c_double, _c.c_int, _c.c_int, _vp, _vp, _vp, _vp, _vp, _c.c_int, _vp]),
     "vodb_sample": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float,
                                _c.c_int, _c.c_int, _c.c_uint64, _c.c_uint64, _vp, _vp, _vp, _vp, _c.c_int, _vp]),
+    "vodb_sample_results": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float,
+                                       _c.c_int, _c.c_int, _c.c_uint64, _c.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _vp]),
     "vodb_plan_scan": (_c.c_int, [_c.c_int64, _c.c_int, _c.c_int, _c.c_int, _vp, _vp, _c.c_int]),
     "vodb_retrieve_sample": (_c.c_int, [_vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _vp, _c.c_int,
                                         _c.c_int, _c.c_int, _c.c_float, _c.c_int, _c.c_int, _c.c_uint64, _c.c_uint64,

@@ -349,8 +349,21 @@ int choose_cap(int nq, int k) {
   return (int)cap;
 }
 
-int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes) {
+// The candidate lists, the query staging and the overflow flag are per store, so the kernels of two calls must not
+// overlap. Calls on one stream are ordered by the stream; a call that arrives on a DIFFERENT stream than its
+// predecessor (a torch side stream after the default stream, the server thread next to the training thread) first
+// waits for the device to drain. Rare by construction, and the only host-blocking point of the asynchronous path.
+int order_streams(vodb_store* s, cudaStream_t st) {
+  if (s->last_stream_set && s->last_stream != st) VODB_CUDA_CHECK(cudaDeviceSynchronize());
+  s->last_stream = st;
+  s->last_stream_set = true;
+  return VODB_OK;
+}
+
+int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes, cudaStream_t st) {
   Workspace& w = s->ws;
+  int rc_order = order_streams(s, st);
+  if (rc_order != VODB_OK) return rc_order;
   int cap = choose_cap(nq, k);
   // lists are laid out [nq, cap] with the cap of THIS call as row stride (a larger stride left over from an earlier
   // call with another k would only spread the lists over more cache lines)
@@ -375,7 +388,8 @@ int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes) {
   if (!w.overflow) {
     VODB_CUDA_CHECK(cudaMalloc(&w.overflow, sizeof(int)));
     VODB_CUDA_CHECK(cudaMalloc(&w.term_any, kTermSlots * sizeof(int)));
-    VODB_CUDA_CHECK(cudaMemset(w.overflow, 0, sizeof(int)));
+    // on the call's stream: a legacy-stream memset is not ordered against work on a non-blocking stream
+    VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
     VODB_CUDA_CHECK(cudaMallocHost(&w.overflow_host, sizeof(int)));
   }
   // staged queries: rows padded to a multiple of 256 so that any TMA box is in bounds; zero filled
@@ -385,7 +399,7 @@ int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes) {
     if (w.q_stage) cudaFree(w.q_stage);
     w.q_stage = nullptr;
     VODB_CUDA_CHECK(cudaMalloc(&w.q_stage, need));
-    VODB_CUDA_CHECK(cudaMemset(w.q_stage, 0, need));
+    VODB_CUDA_CHECK(cudaMemsetAsync(w.q_stage, 0, need, st));
     w.q_stage_bytes = need;
   }
   size_t need_in = (size_t)nq * s->dim * q_elem_bytes;
@@ -722,6 +736,9 @@ int vodb_store_add(vodb_store* s, const void* rows, int src_dtype, int src_on_de
   VODB_REQUIRE(src_dtype == VODB_F32 || src_dtype == VODB_BF16 || src_dtype == VODB_F16, "vodb_store_add: bad src dtype %d", src_dtype);
   if (n == 0) return VODB_OK;
   VODB_REQUIRE(rows != nullptr, "vodb_store_add: rows is NULL");
+  // append or overwrite only (faiss `index.add` appends): rows in a gap would be searchable uninitialised memory
+  VODB_REQUIRE(row0 <= s->n_added, "vodb_store_add: row0=%lld leaves a gap after the %lld rows added so far (add blocks in order)",
+               (long long)row0, (long long)s->n_added);
   DeviceGuard guard(s->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t esz = dtype_size(src_dtype);
@@ -758,6 +775,8 @@ int vodb_store_fill_synthetic(vodb_store* s, uint64_t seed, int64_t row0, int64_
   VODB_REQUIRE(s != nullptr, "vodb_store_fill_synthetic: store is NULL");
   std::lock_guard<std::mutex> store_lock(s->mu);
   VODB_REQUIRE(n >= 0 && row0 >= 0 && row0 + n <= s->n_rows, "vodb_store_fill_synthetic: rows outside the store");
+  VODB_REQUIRE(row0 <= s->n_added, "vodb_store_fill_synthetic: row0=%lld leaves a gap after the %lld rows added so far",
+               (long long)row0, (long long)s->n_added);
   DeviceGuard guard(s->device);
   char* dst = reinterpret_cast<char*>(s->data) + (size_t)row0 * s->pitch * dtype_size(s->dtype);
   int rc = launch_fill_synthetic(dst, s->dtype, s->dim, s->pitch, seed, s->row_offset + row0, n, unit_norm,
@@ -816,7 +835,7 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
   }
   DeviceGuard guard(s->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  rc = ensure_workspace(s, nq, k, dtype_size(q_dtype));
+  rc = ensure_workspace(s, nq, k, dtype_size(q_dtype), st);
   if (rc != VODB_OK) return rc;
   Workspace& w = s->ws;
   const void* q_dev = nullptr;
@@ -934,7 +953,7 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
   }
   DeviceGuard guard(s->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  rc = ensure_workspace(s, nq, k, dtype_size(q_dtype));
+  rc = ensure_workspace(s, nq, k, dtype_size(q_dtype), st);
   if (rc != VODB_OK) return rc;
   Workspace& w = s->ws;
   const void* q_dev = nullptr;
@@ -943,6 +962,7 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
 
   // every rank calls this the same number of times: the epoch (and its parity = buffer half) stay in lockstep
   x->epoch += 1;
+  if (x->epoch == 0) x->epoch = 2;  // 32-bit wrap: 0 is the tag of a zero-initialised buffer; 2 keeps the parity sequence
   const int parity = (int)(x->epoch & 1u);
   ExchangeDst xd{};
   xd.world = x->world;
@@ -1203,6 +1223,74 @@ int vodb_sample(int device, const float* scores, const uint8_t* labels, const fl
   return rc;
 }
 
+// sample_search_results (core/sample.py:22-84) for host arrays in ONE call: labeled priority sampling of the [B,K]
+// retrieved scores, then the gathers of ids / scores at the picks and max_sampling_id (sample.py:57-71) by the same
+// gather kernel the retrieve->sample chain uses. One packed upload, one packed download.
+int vodb_sample_results(int device, const float* scores, const int64_t* indices, const uint8_t* labels,
+                        const float* noise, int B, int K, int k_positive, int k_total, float temperature, int max_support, int quirks, uint64_t seed,
+                        uint64_t offset, int64_t* out_idx, float* out_scores, float* out_logw, uint8_t* out_labels,
+                        float* out_lse, float* out_msid, int64_t* out_local, void* stream) {
+  VODB_REQUIRE(B >= 0 && K >= 1 && K <= 8192, "vodb_sample_results: bad shape [%d, %d] (1 <= K <= 8192)", B, K);
+  VODB_REQUIRE(k_total >= 0 && k_positive >= 0 && k_positive <= k_total,
+               "vodb_sample_results: need 0 <= k_positive <= k_total (got %d, %d)", k_positive, k_total);
+  if (B == 0) return VODB_OK;
+  VODB_REQUIRE(scores && indices && out_idx && out_scores && out_logw && out_labels && out_lse && out_msid,
+               "vodb_sample_results: NULL pointer");
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    set_error("cudaSetDevice(%d) failed", device);
+    return VODB_ECUDA;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t nBK = (size_t)B * K, nBk = (size_t)B * k_total;
+  // inputs [indices i64 | scores f32 | labels u8], outputs [idx i64 | local i64 | scores f32 | logw f32 | lse | msid | labels u8]
+  const size_t i_idx = 0, i_sc = i_idx + nBK * 8, i_noise = i_sc + nBK * 4, i_lab = i_noise + (noise ? nBK * 4 : 0);
+  const size_t in_bytes = (i_lab + (labels ? nBK : 0) + 7) / 8 * 8;
+  const size_t o_idx = in_bytes, o_local = o_idx + nBk * 8, o_sc = o_local + nBk * 8, o_logw = o_sc + nBk * 4;
+  const size_t o_lse = o_logw + nBk * 4, o_msid = o_lse + (size_t)B * 8, o_olab = o_msid + (size_t)B * 4;
+  const size_t total = o_olab + nBk + 16;
+  CallScratch& cs = call_scratch(device);
+  std::lock_guard<std::mutex> lock(cs.mu);
+  char* d = scratch_reserve(cs, total, "vodb_sample_results");
+  if (!d) return VODB_ENOMEM;
+  int max_sup = max_support;
+  if (max_sup >= 0 && max_sup < k_total) max_sup = k_total;  // sample.py:133-135
+  int rc = VODB_OK;
+  cudaError_t e = cudaMemcpyAsync(d + i_idx, indices, nBK * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + i_sc, scores, nBK * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && labels) e = cudaMemcpyAsync(d + i_lab, labels, nBK, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && noise) e = cudaMemcpyAsync(d + i_noise, noise, nBK * 4, cudaMemcpyHostToDevice, st);
+  const uint8_t* d_lab = labels ? reinterpret_cast<const uint8_t*>(d + i_lab) : nullptr;
+  const float* d_noise = noise ? reinterpret_cast<const float*>(d + i_noise) : nullptr;
+  if (e == cudaSuccess)
+    rc = launch_sample(reinterpret_cast<const float*>(d + i_sc), d_lab, d_noise, B, K, k_positive, k_total,
+                       /*normalized=*/1, temperature, max_sup, quirks, seed, offset, reinterpret_cast<int64_t*>(d + o_local),
+                       reinterpret_cast<float*>(d + o_logw), reinterpret_cast<uint8_t*>(d + o_olab),
+                       reinterpret_cast<float*>(d + o_lse), st);
+  if (e == cudaSuccess && rc == VODB_OK)
+    rc = launch_gather_picks(reinterpret_cast<const float*>(d + i_sc), reinterpret_cast<const int64_t*>(d + i_idx), d_lab, B,
+                             K, k_total, reinterpret_cast<const int64_t*>(d + o_local),
+                             reinterpret_cast<const uint8_t*>(d + o_olab), reinterpret_cast<int64_t*>(d + o_idx),
+                             reinterpret_cast<float*>(d + o_sc), reinterpret_cast<float*>(d + o_msid), st);
+  // outputs are contiguous on the device: one copy into the pinned-or-pageable host block would need a host staging
+  // buffer; the seven arrays are small ([B,k_total]), so they are copied one by one and synchronised once
+  if (e == cudaSuccess && rc == VODB_OK && nBk) {
+    e = cudaMemcpyAsync(out_idx, d + o_idx, nBk * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out_local) e = cudaMemcpyAsync(out_local, d + o_local, nBk * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d + o_sc, nBk * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_logw, d + o_logw, nBk * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_labels, d + o_olab, nBk, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess && rc == VODB_OK) e = cudaMemcpyAsync(out_lse, d + o_lse, (size_t)B * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == VODB_OK) e = cudaMemcpyAsync(out_msid, d + o_msid, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_error("vodb_sample_results: %s", cudaGetErrorString(e));
+    return VODB_ECUDA;
+  }
+  return rc;
+}
+
 // The RealmCollate chain for the dense-only flow in ONE call (realm_collate.py:101-122 -> core/sample.py:22-84):
 // search top_k -> label the retrieved ids against the gold ids -> labeled priority sampling of k_total ->
 // gather ids / scores at the picks + max_sampling_id. Only the [nq, k_total] result crosses PCIe (one packed copy).
@@ -1230,7 +1318,7 @@ int vodb_retrieve_sample(vodb_store* s, const void* queries, int q_dtype, int q_
   }
   DeviceGuard guard(s->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  rc = ensure_workspace(s, nq, top_k, dtype_size(q_dtype));
+  rc = ensure_workspace(s, nq, top_k, dtype_size(q_dtype), st);
   if (rc != VODB_OK) return rc;
   Workspace& w = s->ws;
 

@@ -160,6 +160,10 @@ struct vodb_store {
   alignas(64) unsigned char tmap_planes[128];
   bool tmap_planes_valid = false;
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // stream of the previous call that touched the workspace: a call arriving on another stream first waits for
+  // everything enqueued so far (the lists / staging buffers are shared), api.cu order_streams
+  cudaStream_t last_stream = nullptr;
+  bool last_stream_set = false;
   // optional per-kernel timing (vodb_store_set_profiling): events recorded around every scan launch
   bool profiling = false;
   void* prof = nullptr;  // vodb::ProfileState*

@@ -143,42 +143,62 @@ def sample_search_results(
     max_support_size: None | int = None,
     seed: None | int = None,
     offset: int = 0,
+    noise: None | np.ndarray = None,
     fix_truncation: bool = False,
     device: int = 0,
 ) -> PrioritySampledSections:
-    """Sample the positive and negative sections using per-label priority sampling (sample.py:22-84)."""
-    total = total or search_results.shape[-1]
-    max_pos_sections = max_pos_sections or total
+    """Sample the positive and negative sections using per-label priority sampling (sample.py:22-84).
 
-    indices_ref: np.ndarray = search_results.indices
-    scores_ref: np.ndarray = search_results.scores
-    if search_results.labels is None:
-        labels_ref = np.zeros_like(search_results.scores, dtype=np.bool_)
-    else:
-        labels_ref = search_results.labels > 0
+    One `vodb_sample_results` call: the sampler kernel draws the picks, the gather kernel of the retrieve->sample
+    chain (csrc/chain.cu) reads ids / scores at the picks and counts `max_sampling_id` on the device. Only the
+    per-engine `raw_scores`, which never go to the GPU, are gathered here from the returned positions.
+    """
+    lib = _lib.load()
+    _lib.require_gpu()
+    retrieved = np.asarray(search_results.scores)
+    if retrieved.ndim != 2:
+        raise ValueError(f"Expected 2D scores, got {retrieved.ndim}D")
+    B, K = retrieved.shape
+    k_total = int(total or K)
+    k_positive = int(max_pos_sections or k_total)
+    if k_positive > k_total:
+        raise ValueError(f"k_positive={k_positive} > k_total={k_total} (the reference writes out of bounds here)")
+    support = max_support_size or -1
+    s32 = np.ascontiguousarray(retrieved, dtype=np.float32)
+    ids64 = np.ascontiguousarray(search_results.indices, dtype=np.int64)
+    positives = None if search_results.labels is None else np.ascontiguousarray(np.asarray(search_results.labels) > 0, dtype=np.uint8)
+    exp1 = None if noise is None else np.ascontiguousarray(noise, dtype=np.float32)
+    if exp1 is not None and exp1.shape != retrieved.shape:
+        raise ValueError(f"noise shape {exp1.shape} != scores shape {retrieved.shape}")
+    if seed is None and exp1 is None:
+        seed = _draw_seed()
 
-    local_ids, log_weights, labels, constants = labeled_priority_sampling(
-        scores=scores_ref, labels=labels_ref, k_positive=max_pos_sections, k_total=total, normalized=True,
-        temperature=temperature, max_support_size=max_support_size, seed=seed, offset=offset,
-        fix_truncation=fix_truncation, device=device,
-    )
+    picked_ids = np.empty((B, k_total), np.int64)
+    positions = np.empty((B, k_total), np.int64)
+    picked_scores = np.empty((B, k_total), np.float32)
+    log_weights = np.empty((B, k_total), np.float32)
+    picked_labels = np.empty((B, k_total), np.uint8)
+    lse = np.zeros((B, 2), np.float32)
+    msid = np.zeros(B, np.float32)
+    rc = lib.vodb_sample_results(int(device), s32.ctypes.data, ids64.ctypes.data,
+                                 None if positives is None else positives.ctypes.data,
+                                 None if exp1 is None else exp1.ctypes.data, B, K, k_positive, k_total,
+                                 float(temperature), int(support), 0 if fix_truncation else _lib.QUIRK_INVERTED_SUPPORT,
+                                 int(seed or 0) & (2**64 - 1), int(offset) & (2**64 - 1), picked_ids.ctypes.data,
+                                 picked_scores.ctypes.data, log_weights.ctypes.data, picked_labels.ctypes.data,
+                                 lse.ctypes.data, msid.ctypes.data, positions.ctypes.data, _current_stream_ptr(device))
+    _lib.check(rc, "vodb_sample_results")
 
-    # gather the sampled `indices`, `scores` and raw scores (sample.py:57-64)
-    indices = np.take_along_axis(indices_ref, local_ids, axis=-1)
-    scores = np.take_along_axis(scores_ref, local_ids, axis=-1)
-    sampled_raw_scores = {key: np.take_along_axis(v, local_ids, axis=-1) for key, v in raw_scores.items()}
-
-    # rank of the sampled negative with the smallest score — debugging aid (sample.py:66-71)
-    min_neg_score = np.amin(np.where((labels <= 0) & np.isfinite(scores), scores, np.inf), axis=-1, keepdims=True)
-    larger_than_min_sampled = (labels_ref <= 0) & np.isfinite(scores_ref) & (scores_ref >= min_neg_score)
-    max_sampling_id = np.sum(larger_than_min_sampled.astype(np.float32), axis=-1)
-
+    if retrieved.dtype != np.float32 and retrieved.dtype.kind == "f":  # float64 callers get their own values back
+        picked_scores = np.take_along_axis(retrieved, positions, axis=-1)
+        log_weights, lse = log_weights.astype(retrieved.dtype), lse.astype(retrieved.dtype)
+    per_engine = {name: np.take_along_axis(np.asarray(arr), positions, axis=-1) for name, arr in raw_scores.items()}
     batch_cls = type(search_results) if hasattr(type(search_results), "cast") else RetrievalBatch
     return PrioritySampledSections(
-        batch=batch_cls(indices=indices, scores=scores, labels=labels),
-        max_sampling_id=max_sampling_id,
-        lse_pos=constants[..., 0],
-        lse_neg=constants[..., 1],
+        batch=batch_cls(indices=picked_ids, scores=picked_scores, labels=picked_labels.astype(np.bool_)),
+        max_sampling_id=msid,
+        lse_pos=lse[..., 0],
+        lse_neg=lse[..., 1],
         log_weights=log_weights,
-        raw_scores=sampled_raw_scores,
+        raw_scores=per_engine,
     )

@@ -260,7 +260,9 @@ class MultiGpuStore:
                 all_i = torch.stack([i.to(dev0, non_blocking=True) for _, i in parts])
                 ms, mi = merge_topk_device(all_s, all_i, top_k)
                 out = ms.cpu().numpy(), mi.cpu().numpy()
-            if safe_pass or not any(st.check_async() for st in self.stores if st.ntotal):
+            # read (and clear) EVERY store's sticky flag: a short-circuit would leave stale flags for the next search
+            flags = [st.check_async() for st in self.stores if st.ntotal]
+            if safe_pass or not any(flags):
                 return out
         raise AssertionError("unreachable")
 

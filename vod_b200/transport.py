@@ -215,9 +215,16 @@ class SearchServer:
                     elif op == "search":
                         vectors = _recv_array(conn)
                         scores, indices = self._search(vectors, int(args["top_k"]), args.get("mode"))
-                        conn.send(("ok", None))
-                        _send_array(conn, scores)
-                        _send_array(conn, indices)
+                        scores, indices = np.ascontiguousarray(scores), np.ascontiguousarray(indices)
+                        # one framed reply: status + both array headers, then the two raw buffers. Nothing that can
+                        # fail sits between "ok" and the payload; an I/O error past this point closes the connection
+                        # (the client reconnects) instead of desynchronising the stream with an error tuple
+                        conn.send(("ok", ((scores.dtype.str, scores.shape), (indices.dtype.str, indices.shape))))
+                        try:
+                            conn.send_bytes(memoryview(scores).cast("B"))
+                            conn.send_bytes(memoryview(indices).cast("B"))
+                        except (OSError, ValueError):
+                            return
                     else:
                         conn.send(("error", f"unknown op {op!r}"))
                 except Exception as exc:  # errors travel back like the reference's HTTP 500 + trace (server.py:89-91)
@@ -260,7 +267,10 @@ class RemoteSearch:
             status, msg = conn.recv()
             if status != "ok":
                 raise RuntimeError(f"search server error: {msg}")
-            return _recv_array(conn), _recv_array(conn)
+            out = []
+            for dtype, shape in msg:  # fresh, writable, caller-owned arrays
+                out.append(np.frombuffer(conn.recv_bytes(), dtype=np.dtype(dtype)).reshape(shape).copy())
+            return out[0], out[1]
         except (EOFError, OSError):
             self._conn = None
             raise
