@@ -147,3 +147,28 @@ def test_scan_schedule_headline_shapes():
     assert len(b) - 1 == 7
     cap, b = _plan(12_500_000, 64, 1000)
     assert cap == 65536
+
+
+def test_b200_factory_config_mirrors_the_faiss_config_surface():
+    """`backend: "b200"` config + diff + fingerprint + factory function (src/vod_configs/search.py:110-153,
+    src/vod_search/factory.py:131-190), host logic only."""
+    import pydantic
+    import pytest
+
+    import vod_b200
+
+    cfg = vod_b200.B200FactoryConfig(dtype="float16", devices=[0, 1], metric="inner_product")
+    assert cfg.backend == "b200" and cfg.factory == "Flat" and cfg.metric == 0 and cfg.add_batch_size == 2**18
+    merged = cfg + vod_b200.B200FactoryDiff(mode="tensor3", add_batch_size=1024)
+    assert merged.mode == "tensor3" and merged.add_batch_size == 1024 and merged.dtype == "float16"
+    assert (cfg + None) is cfg
+    assert cfg.fingerprint() != merged.fingerprint()                                   # mode changes the results
+    assert cfg.fingerprint() == cfg.model_copy(update={"serve": False}).fingerprint()  # serving details do not
+    with pytest.raises(pydantic.ValidationError):
+        vod_b200.B200FactoryConfig(metric="l2")
+    with pytest.raises(pydantic.ValidationError):
+        vod_b200.B200FactoryConfig(nprobe=16)  # strict model: unknown keys are rejected like StrictModel does
+    master = vod_b200.build_b200_search([[0.0, 1.0]], config={"backend": "b200", "dtype": "float32"})
+    assert isinstance(master, vod_b200.B200SearchMaster) and master.dtype == "float32" and master.store is None
+    with pytest.raises(ValueError):
+        vod_b200.build_b200_search([[0.0]], config={"factory": "IVF100,Flat"})

@@ -16,6 +16,8 @@ from .hybrid import async_hybrid_search, merge_search_results, normalize_search_
 from .collate import flatten_samples, gather_values_by_indices, replace_negative_indices_
 from .routing import ShardedSearchClient
 from .sharded import MultiGpuStore, ShardedCorpus, ShardedSearcher, shard_bounds
+from .config import B200FactoryConfig, B200FactoryDiff, build_b200_search
+from .zarr_io import ZarrV2Array, open_vectors, write_zarr_v2
 
 __all__ = [
     "B200SearchClient", "B200SearchMaster", "CorpusStore", "DenseRetrievalSampler", "sample_device", "DoNotPickleError", "PrioritySampledSections",
@@ -23,5 +25,6 @@ __all__ = [
     "ShardedSearcher", "async_hybrid_search", "merge_search_results", "normalize_search_scores_",
     "VodbError", "VodbUnavailableError", "build_b200_index", "labeled_priority_sampling", "merge_topk",
     "merge_topk_device", "priority_sampling_1d", "sample_search_results", "shard_bounds",
+    "B200FactoryConfig", "B200FactoryDiff", "build_b200_search", "ZarrV2Array", "open_vectors", "write_zarr_v2",
     "flatten_samples", "gather_values_by_indices", "replace_negative_indices_",
 ]
