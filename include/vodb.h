@@ -125,10 +125,17 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
                 int k, int mode, float* out_scores, int64_t* out_idx, int out_on_device,
                 void* stream);
 
+/* Make the store ready for the tensor-core modes now instead of inside the first such search: a float32 store gets
+ * its three bf16 planes allocated (6 more bytes per element) and brought up to date with the rows added so far;
+ * 16-bit stores need nothing. Returns VODB_ENOMEM when the planes do not fit (the store stays usable with
+ * VODB_MODE_EXACT) — the host code's "auto" mode uses this to choose between TENSOR_X3 and EXACT for float32 stores. */
+int vodb_store_prepare_tensor(vodb_store* s, void* stream);
+
 /* With device outputs vodb_search only enqueues work. If a per-query candidate list overflowed (adversarial
  * row order / massive duplicate scores) a sticky device flag is set: this call synchronises `stream`, returns 1
  * if any search since the last check overflowed (results of those searches are invalid: re-run them with host
- * outputs, which falls back to the overflow-proof schedule), 0 if all were fine, or a negative error code. */
+ * outputs, which falls back to the overflow-proof schedule), 0 if all were fine, or a negative error code.
+ * After vodb_search_sharded the answer covers every rank's shard (see there). */
 int vodb_search_check(vodb_store* s, void* stream);
 
 /* Statistics of the last vodb_search on this store (for bench / tests):
@@ -166,8 +173,12 @@ int vodb_xchg_create(vodb_xchg** out, int device, int rank, int world, int max_n
 int vodb_xchg_connect(vodb_xchg* x, const unsigned char* all_handles /* world * VODB_IPC_HANDLE_BYTES */);
 void vodb_xchg_destroy(vodb_xchg* x);
 /* Like vodb_search over this rank's shard, but out_scores / out_idx receive the MERGED result of all shards (every
- * rank gets the same [nq,k] arrays). `safe` != 0 selects the overflow-proof scan schedule (all ranks must pass the
- * same value): callers that saw vodb_search_check()==1 on ANY rank re-run the batch with safe=1 on ALL ranks. */
+ * rank gets the same [nq,k] arrays). Every rank's overflow flag travels with its list (one more tagged word), and the
+ * merge kernel ORs them, so all ranks agree on whether ANY shard overflowed without a collective:
+ *   - host outputs: the call itself re-runs the batch on the overflow-proof schedule, on all ranks in lockstep;
+ *   - device outputs (enqueue only): vodb_search_check() returns the same answer on every rank; callers that see 1
+ *     re-run the batch with safe=1 on ALL ranks.
+ * `safe` != 0 selects the overflow-proof schedule from the start (all ranks must pass the same value). */
 int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_dtype, int q_on_device, int nq,
                         int k, int mode, int safe, float* out_scores, int64_t* out_idx, int out_on_device,
                         void* stream);

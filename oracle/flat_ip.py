@@ -37,21 +37,24 @@ Q_BLOCK = 4096   # faiss distance_compute_blas_query_bs
 
 def topk_desc_stable(scores: np.ndarray, base: int, k: int) -> tuple[np.ndarray, np.ndarray]:
     """k best of each row of `scores` [Q, n] in (score desc, id asc) order; ids offset by `base`."""
-    n = scores.shape[1]
+    nq, n = scores.shape
     kk = min(k, n)
-    # stable argsort of -scores gives (score desc, column asc)
     if kk < n:
-        # partition first (cheap), keeping every entry tied with the kk-th value so ties resolve by id
-        part = np.partition(scores, n - kk, axis=1)[:, n - kk]
-        order = np.empty((scores.shape[0], kk), np.int64)
-        for q in range(scores.shape[0]):
-            cand = np.nonzero(scores[q] >= part[q])[0]
-            o = np.argsort(-scores[q, cand], kind="stable")[:kk]
-            order[q] = cand[o]
+        # k-th largest value per row, then a (score desc, column asc) sort of the kk selected columns. A row whose
+        # k-th value is tied across the selection boundary must take the tied entries with the smallest columns:
+        # those rows (rare) are redone from every entry >= the k-th value.
+        cand = np.argpartition(scores, n - kk, axis=1)[:, n - kk:]
+        vals = np.take_along_axis(scores, cand, axis=1)
+        order = np.lexsort((cand, -vals), axis=1)
+        cols = np.take_along_axis(cand, order, axis=1)
+        kth = vals.min(axis=1)
+        tied = np.nonzero((scores >= kth[:, None]).sum(axis=1) > kk)[0]
+        for q in tied:
+            c = np.nonzero(scores[q] >= kth[q])[0]
+            cols[q] = c[np.argsort(-scores[q, c], kind="stable")[:kk]]
     else:
-        order = np.argsort(-scores, axis=1, kind="stable")[:, :kk]
-    top = np.take_along_axis(scores, order, axis=1)
-    return top, order + base
+        cols = np.argsort(-scores, axis=1, kind="stable")[:, :kk]
+    return np.take_along_axis(scores, cols, axis=1), cols + base
 
 
 def merge_sorted(s_a, i_a, s_b, i_b, k):
@@ -64,8 +67,56 @@ def merge_sorted(s_a, i_a, s_b, i_b, k):
     return np.take_along_axis(s, order, axis=1), np.take_along_axis(i, order, axis=1)
 
 
-def search(xb: np.ndarray, xq: np.ndarray, k: int, *, row_offset: int = 0) -> tuple[np.ndarray, np.ndarray]:
-    """IndexFlatIP.search restated: returns (scores f32 [Q,k], ids i64 [Q,k])."""
+def _survivors(ip: np.ndarray, tau: np.ndarray, base: int) -> tuple[np.ndarray, np.ndarray]:
+    """Entries of `ip` [Q, n] with score >= tau[q], as padded per-query lists (score -FLT_MAX / id -1 padding).
+    This is the collection step of faiss' heap / reservoir result handlers: a score only enters a query's result
+    set if it beats the current k-th best (`>=` keeps exact ties in play so that (score desc, id asc) stays exact)."""
+    mask = ip >= tau[:, None]
+    counts = mask.sum(axis=1)
+    width = int(counts.max(initial=0))
+    out_s = np.full((ip.shape[0], width), -FLT_MAX, np.float32)
+    out_i = np.full((ip.shape[0], width), -1, np.int64)
+    if width:
+        rows, cols = np.nonzero(mask)  # row-major: grouped by query, columns ascending
+        slot = np.arange(len(rows)) - np.repeat(np.cumsum(counts) - counts, counts)
+        out_s[rows, slot] = ip[rows, cols]
+        out_i[rows, slot] = cols + base
+    return out_s, out_i
+
+
+_POOL = None
+
+
+def _collect(ip, cur_s, cur_i, base, k, threads):
+    """Collection step for one block of scores, query rows spread over `threads` host threads (numpy releases the
+    GIL in the comparisons / sorts; faiss runs the same step under `#pragma omp parallel for` over the queries)."""
+    def one(lo, hi):
+        if (cur_i[lo:hi, -1] < 0).any():   # result sets not full yet: plain top-k of the block
+            s, i = topk_desc_stable(ip[lo:hi], base, k)
+        else:                              # full: only scores that reach the current k-th best can enter
+            s, i = _survivors(ip[lo:hi], cur_s[lo:hi, -1], base)
+        return merge_sorted(cur_s[lo:hi], cur_i[lo:hi], s, i, k) if s.shape[1] else (cur_s[lo:hi], cur_i[lo:hi])
+
+    nq = ip.shape[0]
+    if threads <= 1 or nq < 2 * threads:
+        return one(0, nq)
+    global _POOL
+    if _POOL is None or _POOL._max_workers < threads:
+        import concurrent.futures
+
+        _POOL = concurrent.futures.ThreadPoolExecutor(threads, thread_name_prefix="flat-ip")
+    step = -(-nq // threads)
+    parts = list(_POOL.map(lambda lo: one(lo, min(nq, lo + step)), range(0, nq, step)))
+    return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+
+def search(xb: np.ndarray, xq: np.ndarray, k: int, *, row_offset: int = 0, state=None, threads: int = 1):
+    """IndexFlatIP.search restated: returns (scores f32 [Q,k], ids i64 [Q,k]).
+
+    `state` = (scores, ids) of an earlier call over other rows of the same index: the scan continues from it (used
+    by the benchmark to scan a corpus block by block without holding it in memory); ids in it are global.
+    `threads`: host threads for the result collection (the sgemm uses the BLAS library's own thread pool).
+    """
     xb = np.ascontiguousarray(xb, dtype=np.float32)
     xq = np.ascontiguousarray(xq, dtype=np.float32)
     if xq.ndim != 2:
@@ -73,17 +124,15 @@ def search(xb: np.ndarray, xq: np.ndarray, k: int, *, row_offset: int = 0) -> tu
     if xb.ndim != 2 or xb.shape[1] != xq.shape[1]:
         raise ValueError("dimension mismatch")
     nq, n = xq.shape[0], xb.shape[0]
-    out_s = np.full((nq, k), -FLT_MAX, np.float32)
-    out_i = np.full((nq, k), -1, np.int64)
+    out_s = np.full((nq, k), -FLT_MAX, np.float32) if state is None else np.array(state[0], np.float32)
+    out_i = np.full((nq, k), -1, np.int64) if state is None else np.array(state[1], np.int64)
     for q0 in range(0, nq, Q_BLOCK):
         q1 = min(nq, q0 + Q_BLOCK)
-        cur_s = np.full((q1 - q0, k), -FLT_MAX, np.float32)
-        cur_i = np.full((q1 - q0, k), -1, np.int64)
+        cur_s, cur_i = out_s[q0:q1], out_i[q0:q1]
         for b0 in range(0, n, DB_BLOCK * 64):  # 64 faiss blocks per sgemm call: same math, fewer python trips
             b1 = min(n, b0 + DB_BLOCK * 64)
             ip = xq[q0:q1] @ xb[b0:b1].T  # float32 sgemm
-            s, i = topk_desc_stable(ip, b0 + row_offset, k)
-            cur_s, cur_i = merge_sorted(cur_s, cur_i, s, i, k)
+            cur_s, cur_i = _collect(ip, cur_s, cur_i, b0 + row_offset, k, threads)
         out_s[q0:q1], out_i[q0:q1] = cur_s, cur_i
     return out_s, out_i
 
@@ -92,6 +141,7 @@ def search_f64(xb: np.ndarray, xq: np.ndarray, k: int) -> tuple[np.ndarray, np.n
     """Same search with float64 accumulation (tie classifier / ground truth)."""
     ip = xq.astype(np.float64) @ xb.astype(np.float64).T
     s, i = topk_desc_stable(ip, 0, k)
+    i = i.astype(np.int64)
     if s.shape[1] < k:
         pad = k - s.shape[1]
         s = np.concatenate([s, np.full((s.shape[0], pad), -FLT_MAX)], axis=1)

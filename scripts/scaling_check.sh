@@ -13,4 +13,5 @@ launch 2 p2p 29512
 launch 4 p2p 29514
 launch 8 p2p 29518
 launch 8 nccl 29528
-timeout 600 python -m pytest tests/test_multigpu_gpu.py -q -m gpu --timeout=300 -p no:cacheprovider 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_multigpu_gpu.py -v -m gpu --timeout=600 -p no:cacheprovider > gpurun_out/test_multigpu.log 2>&1
+echo "exit=$? test_multigpu"; tail -8 gpurun_out/test_multigpu.log

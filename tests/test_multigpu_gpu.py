@@ -49,6 +49,40 @@ def _worker(rank: int, world: int, port: int, q):
                 ok, msg = False, "sharded tensor-mode result differs from the single-shard result"
             if not (np.array_equal(si2, a[3]) and np.array_equal(ss2, a[2])):
                 ok, msg = False, "sharded exact-mode result differs from the single-shard result"
+        # the drop-in client over the sharded corpus (host buffers, every rank in lockstep): the last shard of an
+        # adversarially ordered corpus overflows its lists on the fast schedule; the overflow flag travels with the
+        # exchanged lists, so ALL ranks re-run on the overflow-proof schedule inside the call, in step
+        if ok:
+            from oracle import flat_ip
+
+            n2 = 150_000 * world
+            adv = np.zeros((n2, 64), np.float32)
+            adv[:, 0] = (np.arange(n2) // 64) % 256
+            adv[:, 1] = np.arange(n2) // (64 * 256)
+            # only the last shard climbs (-> its lists overflow); the others hold ordinary rows with low, varied scores
+            arng = np.random.default_rng(11)
+            adv[: n2 - 150_000, :2] = 0.0
+            adv[: n2 - 150_000, 2:] = arng.integers(-3, 4, size=(n2 - 150_000, 62)).astype(np.float32)
+            aq = np.zeros((3, 64), np.float32)
+            aq[:, 0], aq[:, 1] = 1.0, 256.0
+            aq[:, 2:] = arng.integers(-2, 3, size=(3, 62)).astype(np.float32)
+            corpus = vod_b200.ShardedCorpus(n2, 64, dtype="bfloat16", device=rank, rank=rank, world_size=world,
+                                            exchange="p2p", max_queries=64, max_k=100)
+            corpus.add_global(adv, 0)
+            with vod_b200.B200SearchMaster(store=corpus, serve=False, mode="tensor") as master:
+                for rep in range(2):
+                    res = master.get_client().search(vector=aq, top_k=100)
+                    fell_back = corpus.store.stats()["safe_fallback"] == 1
+                    rs, ri = flat_ip.search(adv, aq, 100)
+                    if not (np.array_equal(res.indices, ri) and np.array_equal(res.scores, rs)):
+                        ok, msg = False, f"sharded client result differs from the oracle on the adversarial corpus (rep {rep})"
+                    if not fell_back:
+                        ok, msg = False, f"rank {rank} did not re-run on the overflow-proof schedule (rep {rep})"
+                ds, di = corpus.search_device(torch.from_numpy(aq).cuda(), 100, mode="tensor")
+                torch.cuda.synchronize()
+                if not corpus.any_overflow():  # asynchronous path: every rank must learn about the overflow
+                    ok, msg = False, f"rank {rank}: any_overflow() missed another shard's overflow"
+            corpus.close()
         dist.barrier()
     except Exception as exc:  # report instead of hanging the other rank
         ok, msg = False, f"{type(exc).__name__}: {exc}"

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "vodb_store_device": (_c.c_int, [_vp]),
     "vodb_store_bytes": (_c.c_int64, [_vp]),
     "vodb_search": (_c.c_int, [_vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _vp, _vp, _c.c_int, _vp]),
+    "vodb_store_prepare_tensor": (_c.c_int, [_vp, _vp]),
     "vodb_search_check": (_c.c_int, [_vp, _vp]),
     "vodb_search_stats": (_c.c_int, [_vp, _c.POINTER(_c.c_int64)]),
     "vodb_store_set_profiling": (_c.c_int, [_vp, _c.c_int]),

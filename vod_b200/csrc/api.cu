@@ -386,11 +386,11 @@ int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes, cudaStream_
   }
   w.cap = cap;
   if (!w.overflow) {
-    VODB_CUDA_CHECK(cudaMalloc(&w.overflow, sizeof(int)));
+    VODB_CUDA_CHECK(cudaMalloc(&w.overflow, 2 * sizeof(int)));
     VODB_CUDA_CHECK(cudaMalloc(&w.term_any, kTermSlots * sizeof(int)));
     // on the call's stream: a legacy-stream memset is not ordered against work on a non-blocking stream
-    VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
-    VODB_CUDA_CHECK(cudaMallocHost(&w.overflow_host, sizeof(int)));
+    VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, 2 * sizeof(int), st));
+    VODB_CUDA_CHECK(cudaMallocHost(&w.overflow_host, 2 * sizeof(int)));
   }
   // staged queries: rows padded to a multiple of 256 so that any TMA box is in bounds; zero filled
   size_t rows_pad = ((size_t)nq + 255) / 256 * 256;
@@ -616,7 +616,8 @@ char* scratch_reserve(CallScratch& cs, size_t bytes, const char* who) {
 struct vodb_xchg {
   int device = 0, rank = 0, world = 1;
   int max_nq = 0, max_k = 0;
-  size_t slot = 0;            // elements per (parity, source rank) slot = max_nq * max_k
+  size_t slot = 0;            // entries per (parity, source rank) slot = max_nq * max_k
+  size_t slot_words = 0;      // 8-byte words per slot: 3 per entry + the overflow-flag word (padded to 8 words)
   size_t bytes = 0;
   char* local = nullptr;      // this rank's buffer
   char* peer[kMaxPeers] = {}; // peer-mapped base pointers (peer[rank] == local)
@@ -862,7 +863,7 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
     int flag;
     std::memcpy(&flag, w.out_host + nqk * 12, sizeof(int));
     if (flag == 0) break;
-    VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
+    VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, 2 * sizeof(int), st));
     if (safe) {
       set_error("vodb_search: candidate list overflow in safe mode (internal error)");
       return VODB_ESTATE;
@@ -889,7 +890,8 @@ int vodb_xchg_create(vodb_xchg** out, int device, int rank, int world, int max_n
   if (!x) return VODB_ENOMEM;
   x->device = device; x->rank = rank; x->world = world; x->max_nq = max_nq; x->max_k = max_k;
   x->slot = (size_t)max_nq * max_k;
-  x->bytes = (size_t)2 * world * x->slot * 3 * sizeof(uint64_t);
+  x->slot_words = x->slot * 3 + 8;
+  x->bytes = (size_t)2 * world * x->slot_words * sizeof(uint64_t);
   cudaError_t e = cudaMalloc(&x->local, x->bytes);
   if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->bytes);
   cudaIpcMemHandle_t h;
@@ -960,37 +962,68 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
   rc = upload_queries(s, queries, q_dtype, q_on_device, nq, st, &q_dev);
   if (rc != VODB_OK) return rc;
 
-  // every rank calls this the same number of times: the epoch (and its parity = buffer half) stay in lockstep
-  x->epoch += 1;
-  if (x->epoch == 0) x->epoch = 2;  // 32-bit wrap: 0 is the tag of a zero-initialised buffer; 2 keeps the parity sequence
-  const int parity = (int)(x->epoch & 1u);
-  ExchangeDst xd{};
-  xd.world = x->world;
-  xd.rank = x->rank;
-  xd.epoch = x->epoch;
-  for (int r = 0; r < x->world; ++r)
-    xd.peer_ll[r] = reinterpret_cast<uint64_t*>(x->peer[r]) + ((size_t)parity * x->world + x->rank) * x->slot * 3;
-  if (s->n_added > 0) {
-    rc = run_scan(s, q_dev, q_dtype, nq, k, mode, safe != 0, nullptr, nullptr, st, &xd);
-  } else {
-    // an empty shard (more ranks than row blocks) contributes an all-padding list
-    VODB_CUDA_CHECK(cudaMemsetAsync(w.cnt, 0, (size_t)nq * sizeof(int), st));
-    rc = launch_select(w.cand_s, w.cand_i, w.cnt, w.tau, w.cap, nq, k, true, nullptr, nullptr, s->row_offset, st, &xd);
-  }
-  if (rc != VODB_OK) return rc;
   const size_t nqk = (size_t)nq * k;
   float* o_s = out_on_device ? out_scores : reinterpret_cast<float*>(w.out_pack + nqk * 8);
   int64_t* o_i = out_on_device ? out_idx : reinterpret_cast<int64_t*>(w.out_pack);
-  const uint64_t* gll = reinterpret_cast<const uint64_t*>(x->local) + (size_t)parity * x->world * x->slot * 3;
-  rc = launch_merge_exchange(gll, x->epoch, x->world, x->slot, nq, k, o_s, o_i, st);
-  if (rc != VODB_OK) return rc;
-  if (!out_on_device) {
-    VODB_CUDA_CHECK(cudaMemcpyAsync(w.out_host, w.out_pack, nqk * 12, cudaMemcpyDeviceToHost, st));
+  bool safe_run = safe != 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    // every rank calls this the same number of times: the epoch (and its parity = buffer half) stay in lockstep
+    x->epoch += 1;
+    if (x->epoch == 0) x->epoch = 2;  // 32-bit wrap: 0 is the tag of a zero-initialised buffer; 2 keeps the parity sequence
+    const int parity = (int)(x->epoch & 1u);
+    ExchangeDst xd{};
+    xd.world = x->world;
+    xd.rank = x->rank;
+    xd.epoch = x->epoch;
+    xd.overflow = w.overflow;
+    for (int r = 0; r < x->world; ++r) {
+      xd.peer_ll[r] = reinterpret_cast<uint64_t*>(x->peer[r]) + ((size_t)parity * x->world + x->rank) * x->slot_words;
+      xd.peer_flag[r] = xd.peer_ll[r] + x->slot * 3;
+    }
+    if (s->n_added > 0) {
+      rc = run_scan(s, q_dev, q_dtype, nq, k, mode, safe_run, nullptr, nullptr, st, &xd);
+    } else {
+      // an empty shard (more ranks than row blocks) contributes an all-padding list
+      VODB_CUDA_CHECK(cudaMemsetAsync(w.cnt, 0, (size_t)nq * sizeof(int), st));
+      rc = launch_select(w.cand_s, w.cand_i, w.cnt, w.tau, w.cap, nq, k, true, nullptr, nullptr, s->row_offset, st, &xd);
+    }
+    if (rc != VODB_OK) return rc;
+    const uint64_t* gll = reinterpret_cast<const uint64_t*>(x->local) + (size_t)parity * x->world * x->slot_words;
+    rc = launch_merge_exchange(gll, x->epoch, x->world, x->slot_words, x->slot * 3, nq, k, o_s, o_i, w.overflow + 1, st);
+    if (rc != VODB_OK) return rc;
+    if (out_on_device) return VODB_OK;  // asynchronous: the caller polls vodb_search_check (same answer on every rank)
+    // host outputs: results + the all-shard overflow flag in ONE copy; the flag is the OR over every rank's shard, so
+    // all ranks take the same branch here and the re-run on the overflow-proof schedule stays in lockstep
+    VODB_CUDA_CHECK(cudaMemcpyAsync(w.out_pack + nqk * 12, w.overflow + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    VODB_CUDA_CHECK(cudaMemcpyAsync(w.out_host, w.out_pack, nqk * 12 + sizeof(int), cudaMemcpyDeviceToHost, st));
     VODB_CUDA_CHECK(cudaStreamSynchronize(st));
-    std::memcpy(out_idx, w.out_host, nqk * 8);
-    std::memcpy(out_scores, w.out_host + nqk * 8, nqk * 4);
+    int flag;
+    std::memcpy(&flag, w.out_host + nqk * 12, sizeof(int));
+    if (flag == 0) break;
+    VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, 2 * sizeof(int), st));
+    if (safe_run) {
+      set_error("vodb_search_sharded: candidate list overflow in safe mode (internal error)");
+      return VODB_ESTATE;
+    }
+    safe_run = true;
   }
+  std::memcpy(out_idx, w.out_host, nqk * 8);
+  std::memcpy(out_scores, w.out_host + nqk * 8, nqk * 4);
   return VODB_OK;
+}
+
+int vodb_store_prepare_tensor(vodb_store* s, void* stream) {
+  VODB_REQUIRE(s != nullptr, "vodb_store_prepare_tensor: store is NULL");
+  std::lock_guard<std::mutex> store_lock(s->mu);
+  if (!tensor_path_supported(s)) {
+    set_error("vodb_store_prepare_tensor: the driver does not export cuTensorMapEncodeTiled");
+    return VODB_EUNSUPPORTED;
+  }
+  DeviceGuard guard(s->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = order_streams(s, st);
+  if (rc != VODB_OK) return rc;
+  return ensure_planes(s, st);  // no-op for 16-bit stores; VODB_ENOMEM when the planes do not fit
 }
 
 int vodb_search_check(vodb_store* s, void* stream) {
@@ -1000,10 +1033,10 @@ int vodb_search_check(vodb_store* s, void* stream) {
   if (!w.overflow) return 0;
   DeviceGuard guard(s->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  VODB_CUDA_CHECK(cudaMemcpyAsync(w.overflow_host, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
-  VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
+  VODB_CUDA_CHECK(cudaMemcpyAsync(w.overflow_host, w.overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, 2 * sizeof(int), st));
   VODB_CUDA_CHECK(cudaStreamSynchronize(st));
-  return *w.overflow_host != 0 ? 1 : 0;
+  return (w.overflow_host[0] | w.overflow_host[1]) != 0 ? 1 : 0;
 }
 
 int vodb_store_set_profiling(vodb_store* s, int enable) {
@@ -1374,7 +1407,7 @@ int vodb_retrieve_sample(vodb_store* s, const void* queries, int q_dtype, int q_
     int flag;
     std::memcpy(&flag, w.chain_host + o_flag, sizeof(int));
     if (flag == 0) break;
-    VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
+    VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, 2 * sizeof(int), st));
     if (safe) {
       set_error("vodb_retrieve_sample: candidate list overflow in safe mode (internal error)");
       return VODB_ESTATE;

@@ -110,7 +110,8 @@ struct Workspace {
   int* cnt = nullptr;
   float* tau = nullptr;
   int* term_any = nullptr;     // [kTermSlots] per prepare-block bit mask: bit t set = query term t has a nonzero element
-  int* overflow = nullptr;     // device flag: a candidate list ran out of room
+  int* overflow = nullptr;     // device flags: [0] a candidate list of THIS shard ran out of room (sticky);
+                               // [1] some shard of a sharded search did (OR over the ranks, set by the merge kernel)
   int* overflow_host = nullptr;  // pinned mirror
   int nq_cap = 0;        // counters / thresholds allocated for this many queries
   size_t list_elems = 0; // candidate slots allocated in total (>= nq * cap of the current call)
@@ -206,6 +207,10 @@ struct ExchangeDst {
   int rank;
   uint32_t epoch;
   uint64_t* peer_ll[kMaxPeers];  // peer r's gather buffer, slot `rank`, current parity: [nq*k][3] words
+  // one more tagged word per (parity, source rank) behind the entries: epoch<<32 | this shard's overflow flag, so that
+  // every rank learns from the exchange itself whether ANY shard overflowed (all ranks then re-run in lockstep)
+  uint64_t* peer_flag[kMaxPeers];
+  const int* overflow;           // this shard's sticky flag (Workspace::overflow[0])
 };
 
 int launch_score_exact(const SegmentArgs& a, int sm_count, cudaStream_t stream);
@@ -217,8 +222,9 @@ int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap,
                   float* out_s, int64_t* out_i, int64_t row_offset, cudaStream_t stream,
                   const ExchangeDst* xd = nullptr, int expected_n = 0);
 // merge of the gathered per-rank lists; waits for every entry's epoch tag (see ExchangeDst)
-int launch_merge_exchange(const uint64_t* gather_ll, uint32_t epoch, int world, size_t slot_elems, int nq, int k,
-                          float* out_s, int64_t* out_i, cudaStream_t stream);
+// slot_words = words per (parity, source rank) slot (entries + the flag word at offset flag_word)
+int launch_merge_exchange(const uint64_t* gather_ll, uint32_t epoch, int world, size_t slot_words, size_t flag_word, int nq,
+                          int k, float* out_s, int64_t* out_i, int* overflow_any, cudaStream_t stream);
 int launch_merge(const float* scores, const int64_t* idx, int n_lists, int nq, int k_in, int k_out, float* out_s,
                  int64_t* out_i, cudaStream_t stream);
 

@@ -261,6 +261,12 @@ select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __r
     // fused exchange: store this shard's result into every rank's gather buffer (own rank included) as
     // tagged 8-byte words; nothing else is needed to publish it
     const uint64_t tag = (uint64_t)xd.epoch << 32;
+    if (q == 0 && threadIdx.x == 0) {
+      // every scoring kernel of this search has completed (stream order): the shard's overflow flag is final
+      const uint64_t f = tag | (uint64_t)(*reinterpret_cast<const volatile int*>(xd.overflow) != 0 ? 1u : 0u);
+      for (int r = 0; r < xd.world; ++r)
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(xd.peer_flag[r]), "l"(f) : "memory");
+    }
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
       const float sv = (j < n_sel) ? ord_to_float(sel_o[j]) : VODB_NEG_FLT_MAX;
       const int64_t iv = (j < n_sel) ? (int64_t)sel_i[j] + row_offset : (int64_t)-1;
@@ -337,8 +343,9 @@ __device__ __forceinline__ uint64_t ll_wait_word(const uint64_t* p, uint32_t epo
 }
 
 __global__ void __launch_bounds__(kSelThreads)
-merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, int world, size_t slot_elems, int nq,
-                      int k, int P, float* __restrict__ out_s, int64_t* __restrict__ out_i) {
+merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, int world, size_t slot_words,
+                      size_t flag_word, int nq, int k, int P, float* __restrict__ out_s, int64_t* __restrict__ out_i,
+                      int* __restrict__ overflow_any) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ SelectSmem<int64_t> sm;
   int64_t* sel_i = reinterpret_cast<int64_t*>(dyn);
@@ -347,9 +354,12 @@ merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, in
   pdl_wait();  // this rank's final select (which also filled slot `rank` of the local gather buffer) is complete
   const int q = blockIdx.x;
   const int n = world * k;
+  if (q == 0 && threadIdx.x < world) {  // did any shard overflow? (sticky, read back by the host with the results)
+    if ((uint32_t)ll_wait_word(gather_ll + (size_t)threadIdx.x * slot_words + flag_word, epoch) != 0u) *overflow_any = 1;
+  }
   auto entry = [&](int i) -> const uint64_t* {
     int l = i / k, j = i - l * k;
-    return gather_ll + ((size_t)l * slot_elems + (size_t)q * k + j) * 3;
+    return gather_ll + (size_t)l * slot_words + ((size_t)q * k + j) * 3;
   };
   auto load_s = [&](int i) -> float { return __uint_as_float((uint32_t)ll_wait_word(entry(i), epoch)); };
   auto load_i = [&](int i) -> int64_t {
@@ -387,12 +397,12 @@ int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap,
   return VODB_OK;
 }
 
-int launch_merge_exchange(const uint64_t* gather_ll, uint32_t epoch, int world, size_t slot_elems, int nq, int k,
-                          float* out_s, int64_t* out_i, cudaStream_t stream) {
+int launch_merge_exchange(const uint64_t* gather_ll, uint32_t epoch, int world, size_t slot_words, size_t flag_word, int nq,
+                          int k, float* out_s, int64_t* out_i, int* overflow_any, cudaStream_t stream) {
   int P = pow2ceil(k);
   size_t smem = (size_t)P * (sizeof(int64_t) + sizeof(uint32_t));
   VODB_CUDA_CHECK(launch_pdl(merge_exchange_kernel, dim3(nq), dim3(kSelThreads), smem, stream, gather_ll, epoch, world,
-                             slot_elems, nq, k, P, out_s, out_i));
+                             slot_words, flag_word, nq, k, P, out_s, out_i, overflow_any));
   return VODB_OK;
 }
 

@@ -125,6 +125,7 @@ class CorpusStore:
         _lib.check(self._lib.vodb_store_create(ctypes.byref(handle), int(device), int(n_rows), int(dim), code,
                                               int(row_offset)), "vodb_store_create")
         self._h: ctypes.c_void_p | None = handle
+        self._planes_fit: bool | None = None  # float32 store: do the bf16 planes of the tensor modes fit? (decided once)
         self.n_rows, self.dim, self.dtype_code, self.device, self.row_offset = int(n_rows), int(dim), code, int(device), int(row_offset)
 
     # -- lifecycle
@@ -194,15 +195,27 @@ class CorpusStore:
         return out
 
     # -- search
+    def prepare_tensor(self) -> bool:
+        """Build what the tensor-core modes need ahead of the first search (float32 store: its bf16 planes, +6 bytes
+        per element). False when the planes do not fit in HBM; the store then serves `mode="exact"` only."""
+        rc = self._lib.vodb_store_prepare_tensor(self.handle, _current_stream_ptr(self.device))
+        if rc == -3:  # VODB_ENOMEM
+            return False
+        _lib.check(rc, "vodb_store_prepare_tensor")
+        return True
+
     def _mode(self, mode: str | int | None, q_code: int | None = None) -> int:
-        """Scoring mode. "auto": fp32 store -> fp32 CUDA-core kernel; 16-bit store -> tensor cores, with the query
-        kept exact: one term when the queries already are in the store dtype, else three 16-bit terms (full fp32
-        mantissa, IndexFlatIP parity at the fp32 tolerance). "tensor" forces one term (queries rounded).
-        "tensor3" on an fp32 store runs the tensor cores over three bf16 planes of the rows (same fp32-exact
-        tolerance, 3-4x faster than "exact", +6 bytes per stored element — hence opt-in)."""
+        """Scoring mode. "auto" keeps the float32 query exact on the tensor cores: a 16-bit store takes one term when
+        the queries already are in the store dtype, else three 16-bit terms (full fp32 mantissa); a float32 store is
+        searched through three bf16 planes of its rows x three query terms ("tensor3": IndexFlatIP parity at the
+        fp32 tolerance, 3-4x faster than the fp32 CUDA-core kernel) when the planes fit in HBM (+6 bytes per stored
+        element, built on first use), and by the CUDA-core kernel ("exact") otherwise. "tensor" forces one term
+        (queries rounded to the store dtype)."""
         if mode is None or mode == "auto":
             if self.dtype_code == _lib.F32:
-                return _lib.MODE_EXACT
+                if self._planes_fit is None:
+                    self._planes_fit = self.prepare_tensor()
+                return _lib.MODE_TENSOR_X3 if self._planes_fit else _lib.MODE_EXACT
             return _lib.MODE_TENSOR if q_code == self.dtype_code else _lib.MODE_TENSOR_X3
         if isinstance(mode, int):
             return mode

@@ -62,6 +62,13 @@ class ShardedSearcher:
         import torch.distributed as dist
 
         scores, ids = self.local_search(queries, top_k)
+        return self.merge_gathered(scores, ids, top_k)
+
+    def merge_gathered(self, scores: typ.Any, ids: typ.Any, top_k: int):
+        """All-gather this rank's [B,k] list and merge the `world` lists (every rank gets the same result)."""
+        import torch
+        import torch.distributed as dist
+
         world = self.world_size()
         if world == 1:
             return scores, ids
@@ -136,12 +143,26 @@ class ShardedCorpus:
         if a < b:
             self.store.add(rows[a - row0:b - row0], row0=a - self.lo)
 
-    def search_device(self, queries: typ.Any, top_k: int, mode: str | None = None, safe: bool = False, out=None):
+    @property
+    def ntotal(self) -> int:
+        """Rows of the whole corpus (all shards), like `index.ntotal` of the reference's IndexShards."""
+        return self.n_total
+
+    @property
+    def device(self) -> int:
+        return self.store.device
+
+    def search_device(self, queries: typ.Any, top_k: int, mode: str | None = None, safe: bool = False, out=None,
+                      exchange: str | None = None):
         """Merged top-k over all shards for CUDA queries; returns (scores [B,k] f32, ids [B,k] i64) CUDA tensors,
-        identical on every rank. Only enqueues work on torch's current stream."""
+        identical on every rank. Only enqueues work on torch's current stream. `exchange` overrides the corpus
+        default for this call ("nccl": all-gather + merge kernel instead of the fused peer-store exchange)."""
         self.mode = mode
-        if self.exchange != "p2p":
+        how = self.exchange if exchange is None or self.world == 1 else exchange
+        if how != "p2p":
             return self._searcher.search(queries, top_k)
+        if self._xchg is None:
+            raise ValueError("this corpus was created without the p2p exchange")
         import torch
 
         from . import _lib
@@ -164,14 +185,61 @@ class ShardedCorpus:
                                            _current_stream_ptr(self.store.device)), "vodb_search_sharded")
         return scores, ids
 
+    def search(self, vectors: np.ndarray, top_k: int, mode: str | int | None = None) -> tuple[np.ndarray, np.ndarray]:
+        """Host path with the `CorpusStore.search` signature, so that a `B200SearchMaster(store=corpus)` /
+        `B200SearchClient` serves the sharded corpus unchanged: numpy [B, dim] in, merged (scores f32 [B,k], ids i64
+        [B,k]) out, H2D / D2H inside the call. SPMD: every rank calls it with the same batch. A list overflow on any
+        shard re-runs the batch on the overflow-proof schedule on all ranks (decided from the exchanged flags)."""
+        from . import _lib
+        from .search import _current_stream_ptr, _np_dtype_code
+
+        q = np.ascontiguousarray(vectors)
+        if q.ndim != 2:
+            raise ValueError(f"Expected 2D array, got {q.ndim}D array")  # server.py:82-83
+        if q.shape[1] != self.dim:
+            raise ValueError(f"query dimension {q.shape[1]} != index dimension {self.dim}")
+        if q.dtype not in (np.float32, np.float16):
+            q = q.astype(np.float32)
+        if self.exchange != "p2p":
+            if self.world == 1:
+                return self.store.search(q, top_k, mode=mode)
+            import torch
+
+            for safe in (False, True):  # unfused path: flags agreed on with an all-reduce
+                if safe:
+                    self.mode = mode
+                    s_np, i_np = self.store.search(q, top_k, mode=mode)  # overflow-proof fallback inside
+                    dev = f"cuda:{self.store.device}"
+                    s, i = self._searcher.merge_gathered(torch.from_numpy(s_np).to(dev), torch.from_numpy(i_np).to(dev), top_k)
+                else:
+                    s, i = self.search_device(torch.from_numpy(q).to(f"cuda:{self.store.device}"), top_k, mode=mode)
+                out = s.cpu().numpy(), i.cpu().numpy()
+                if safe or not self.any_overflow():
+                    return out
+        B = q.shape[0]
+        if B * top_k > self._xchg_limits[0] * self._xchg_limits[1]:
+            raise ValueError("batch x top_k exceeds the exchange buffer (raise max_queries / max_k)")
+        scores = np.empty((B, top_k), np.float32)
+        ids = np.empty((B, top_k), np.int64)
+        code = _np_dtype_code(q)
+        lib = _lib.load()
+        _lib.check(lib.vodb_search_sharded(self.store.handle, self._xchg, q.ctypes.data, code, 0, B, int(top_k),
+                                           self.store._mode(mode, code), 0, scores.ctypes.data, ids.ctypes.data, 0,
+                                           _current_stream_ptr(self.store.device)), "vodb_search_sharded")
+        return scores, ids
+
     def any_overflow(self) -> bool:
-        """True if a candidate list overflowed on ANY rank since the last check (then re-run with safe=True)."""
+        """True if a candidate list overflowed on ANY rank since the last check (then re-run with safe=True). With
+        the fused exchange every rank already holds the OR of all shards' flags (they travel with the lists); the
+        NCCL path agrees on it with an all-reduce."""
+        local = self.store.check_async()
+        if self.world == 1 or self.exchange == "p2p":
+            return bool(local)
         import torch
         import torch.distributed as dist
 
-        flag = torch.tensor([1 if self.store.check_async() else 0], dtype=torch.int32, device=f"cuda:{self.store.device}")
-        if self.world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        flag = torch.tensor([1 if local else 0], dtype=torch.int32, device=f"cuda:{self.store.device}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
         return bool(flag.item())
 
     def close(self) -> None:
