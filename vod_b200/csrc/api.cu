@@ -341,6 +341,8 @@ int pow2ceil_host(int64_t x) {
 
 // candidate-list capacity: room for ~128 k entries, within a ~4 GB budget for the whole batch
 int choose_cap(int nq, int k) {
+  static const char* env_cap = std::getenv("VODB_CAP");  // development knob (schedule sweeps)
+  if (env_cap) return std::max(pow2ceil_host(4LL * k), pow2ceil_host(std::atoll(env_cap)));
   int64_t cap = pow2ceil_host(std::max<int64_t>(128LL * k, 8192));
   cap = std::min<int64_t>(cap, 65536);
   const int64_t budget = 4LL << 30;
@@ -466,7 +468,7 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
   b.push_back(first);
   // growth: expected survivors of a segment = k * seg/before; keep that below cap/8
   double g = std::max(1.0, std::min((double)cap / (8.0 * k), large_batch ? 3.0 : 32.0));
-  if (env_growth && !large_batch) g = std::max(1.0, std::min(g, std::atof(env_growth)));
+  if (env_growth && !large_batch) g = std::max(1.0, std::atof(env_growth));
   if (env_growth_large && large_batch) g = std::max(1.0, std::min((double)cap / (8.0 * k), std::atof(env_growth_large)));
   int64_t cur = first;
   while (cur < n) {

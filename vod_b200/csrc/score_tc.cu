@@ -153,8 +153,30 @@ struct TcParams {
   // kernel with kOnlyIfMultiTerm. Exactly one of them does the work, chosen on the device from term_any; the other
   // finds zero items and retires in a few microseconds.
   int term_policy;
+  // Item order when a corpus tile meets several query tiles (n_qtiles > 1). 0: query tile fastest — every CTA works
+  // on the same one or two corpus tiles at the same moment, so their first loads of a tile reach the L2 together,
+  // before the line has arrived from HBM, and are fetched more than once (ncu: 2.9x the algorithmic DRAM bytes).
+  // > 0: the corpus is walked in blocks of `raster_tiles` tiles (one per CTA / CTA pair, ~30 MB, L2 resident); inside
+  // a block the QUERY tile is the slow index: during the first pass every CTA streams a different corpus tile from
+  // HBM (each line is requested once), the remaining n_qtiles - 1 passes find the block in L2.
+  int raster_tiles;
 };
 constexpr int kTermAlways = 0, kOnlyIfSingleTerm = 1, kOnlyIfMultiTerm = 2;
+
+__device__ __forceinline__ void item_to_tiles(const TcParams& p, int item, int& ct, int& qt) {
+  if (p.raster_tiles <= 0) {
+    ct = item / p.n_qtiles;
+    qt = item - ct * p.n_qtiles;
+    return;
+  }
+  const int per_block = p.raster_tiles * p.n_qtiles;
+  const int blk = item / per_block;
+  const int r = item - blk * per_block;
+  const int c0 = blk * p.raster_tiles;
+  const int bc = min(p.raster_tiles, p.n_ctiles - c0);  // the last block may be short
+  qt = r / bc;
+  ct = c0 + (r - qt * bc);
+}
 
 // Per-warp staging of filter survivors (shared memory). Each epilogue warp owns two small buffers: survivors of
 // item i are pushed with shared-memory atomics into buffer i&1 and appended to the global per-query lists at the
@@ -445,7 +467,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int ct = item / p.n_qtiles, qt = item - ct * p.n_qtiles;
+        int ct, qt;
+        item_to_tiles(p, item, ct, qt);
         const int row0 = (int)(p.row_begin + (int64_t)ct * BM);
         const int q0 = qt * BN;
         for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -454,8 +477,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
             const int nt = (P == 1) ? nt_run : (P - pl);  // query terms multiplied with this plane
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], Cfg::kABytes + (uint32_t)nt * Cfg::kBBytes);
+            // blocked order: the last pass over a block lets its lines go (the next block needs the room)
             tma_load_2d(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC,
-                        pl * p.plane_rows + row0, corpus_policy);
+                        pl * p.plane_rows + row0,
+                        (p.raster_tiles > 0 && qt == p.n_qtiles - 1) ? kEvictFirst : corpus_policy);
 #pragma unroll
             for (int t = 0; t < T; ++t)
               if (t < nt)
@@ -528,7 +553,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
 #pragma unroll
     for (int u = 0; u < kFlushPerLane; ++u) pend.pos[u] = -1;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
-      const int ct = item / p.n_qtiles, qt = item - ct * p.n_qtiles;
+      int ct, qt;
+      item_to_tiles(p, item, ct, qt);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int q0 = qt * BN;
@@ -705,13 +731,15 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       for (int item = pair; item < n_items; item += n_pairs) {
-        const int ct = item / p.n_qtiles, qt = item - ct * p.n_qtiles;
+        int ct, qt;
+        item_to_tiles(p, item, ct, qt);
         const int row0 = (int)(p.row_begin + ((int64_t)ct * 2 + rank) * BM);
         const int q0 = qt * BN + (int)rank * (BN / 2);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-          tma_load_2d_2sm(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC, row0, kEvictLast);
+          tma_load_2d_2sm(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC, row0,
+                          (p.n_qtiles == 1 || (p.raster_tiles > 0 && qt == p.n_qtiles - 1)) ? kEvictFirst : kEvictLast);
           tma_load_2d_2sm(&tmap_query, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kc * KC, q0, kEvictLast);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -754,7 +782,8 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
 #pragma unroll
     for (int u = 0; u < kFlushPerLane; ++u) pend.pos[u] = -1;
     for (int item = pair; item < n_items; item += n_pairs, ++local) {
-      const int ct = item / p.n_qtiles, qt = item - ct * p.n_qtiles;
+      int ct, qt;
+      item_to_tiles(p, item, ct, qt);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int q0 = qt * BN;
@@ -835,6 +864,11 @@ bool pair_kernel_enabled() {
   static const char* env = std::getenv("VODB_TC2");
   return env ? (env[0] != '0') : true;
 }
+// VODB_RASTER=0 restores the query-tile-fastest item order (A/B comparisons)
+bool raster_enabled() {
+  static const char* env = std::getenv("VODB_RASTER");
+  return env ? (env[0] != '0') : true;
+}
 bool use_pair_kernel(const SegmentArgs& a) { return pair_kernel_enabled() && a.terms == 1 && a.planes == 1 && a.nq > 128; }
 // large multi-term batches on a 16-bit store: the pair kernel also runs, for the case that the correction terms
 // turn out empty on the device (see TcParams::term_policy)
@@ -896,6 +930,7 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
   if (items <= 0) return VODB_OK;
   int grid = (int)(items < s->sm_count ? items : s->sm_count);
+  p.raster_tiles = (p.n_qtiles > 1 && raster_enabled()) ? grid : 0;
   VODB_CUDA_CHECK(launch_pdl(score_tc_kernel<BN, T, P>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream,
                              *tmap_store, tmap_q, p));
   return VODB_OK;
@@ -935,6 +970,7 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
   if (items <= 0) return VODB_OK;
   int pairs = (int)std::min<int64_t>(items, s->sm_count / 2);
+  p.raster_tiles = (p.n_qtiles > 1 && raster_enabled()) ? pairs : 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kThreads);

@@ -302,9 +302,13 @@ select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __r
   }
 }
 
-__global__ void __launch_bounds__(kSelThreads)
+// Both merge kernels first copy the world*k_in (score, id) entries of their query into shared memory — one pass over
+// the gathered lists (for the fused exchange: one tagged sys-scope load per word, spinning until the peer's store has
+// landed) — and run the radix select + sort there. `staged` == 0 is the fallback for inputs that do not fit
+// (world*k_in*12 bytes > ~190 KB): every pass then re-reads global memory as the first version did.
+__global__ void __launch_bounds__(1024)
 merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, int n_lists, int nq, int k_in,
-             int k_out, int P, float* __restrict__ out_s, int64_t* __restrict__ out_i) {
+             int k_out, int P, int staged, float* __restrict__ out_s, int64_t* __restrict__ out_i) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ SelectSmem<int64_t> sm;
   int64_t* sel_i = reinterpret_cast<int64_t*>(dyn);
@@ -315,10 +319,25 @@ merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, 
     int l = i / k_in, j = i - l * k_in;
     return ((size_t)l * nq + q) * k_in + j;
   };
-  auto load_s = [&](int i) -> float { return scores[off_of(i)]; };
-  auto load_i = [&](int i) -> int64_t { return idx[off_of(i)]; };
   uint32_t vstar;
-  int n_sel = block_select<int64_t>(load_s, load_i, n, k_out, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar);
+  int n_sel;
+  if (staged) {
+    int64_t* all_i = reinterpret_cast<int64_t*>(dyn + (((size_t)P * 12 + 15) & ~(size_t)15));
+    float* all_s = reinterpret_cast<float*>(all_i + n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const size_t o = off_of(i);
+      all_s[i] = scores[o];
+      all_i[i] = idx[o];
+    }
+    __syncthreads();
+    auto load_s = [&](int i) -> float { return all_s[i]; };
+    auto load_i = [&](int i) -> int64_t { return all_i[i]; };
+    n_sel = block_select<int64_t>(load_s, load_i, n, k_out, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar);
+  } else {
+    auto load_s = [&](int i) -> float { return scores[off_of(i)]; };
+    auto load_i = [&](int i) -> int64_t { return idx[off_of(i)]; };
+    n_sel = block_select<int64_t>(load_s, load_i, n, k_out, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar);
+  }
   __syncthreads();
   for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
     bool ok = j < n_sel && sel_i[j] >= 0;
@@ -342,10 +361,10 @@ __device__ __forceinline__ uint64_t ll_wait_word(const uint64_t* p, uint32_t epo
   }
 }
 
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __launch_bounds__(1024)
 merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, int world, size_t slot_words,
-                      size_t flag_word, int nq, int k, int P, float* __restrict__ out_s, int64_t* __restrict__ out_i,
-                      int* __restrict__ overflow_any) {
+                      size_t flag_word, int nq, int k, int P, int staged, float* __restrict__ out_s,
+                      int64_t* __restrict__ out_i, int* __restrict__ overflow_any) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ SelectSmem<int64_t> sm;
   int64_t* sel_i = reinterpret_cast<int64_t*>(dyn);
@@ -361,14 +380,37 @@ merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, in
     int l = i / k, j = i - l * k;
     return gather_ll + (size_t)l * slot_words + ((size_t)q * k + j) * 3;
   };
-  auto load_s = [&](int i) -> float { return __uint_as_float((uint32_t)ll_wait_word(entry(i), epoch)); };
-  auto load_i = [&](int i) -> int64_t {
-    const uint64_t* e = entry(i);
-    uint64_t lo = ll_wait_word(e + 1, epoch), hi = ll_wait_word(e + 2, epoch);
-    return (int64_t)((lo & 0xffffffffull) | (hi << 32));
-  };
   uint32_t vstar;
-  int n_sel = block_select<int64_t>(load_s, load_i, n, k, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar);
+  int n_sel;
+  if (staged) {
+    int64_t* all_i = reinterpret_cast<int64_t*>(dyn + (((size_t)P * 12 + 15) & ~(size_t)15));
+    float* all_s = reinterpret_cast<float*>(all_i + n);
+    // the three words of an entry are loaded back to back (independent loads in flight together); only a word whose
+    // tag is not there yet is polled
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint64_t* e = entry(i);
+      uint64_t w[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w[j]) : "l"(e + j) : "memory");
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if ((uint32_t)(w[j] >> 32) != epoch) w[j] = ll_wait_word(e + j, epoch);
+      all_s[i] = __uint_as_float((uint32_t)w[0]);
+      all_i[i] = (int64_t)((w[1] & 0xffffffffull) | (w[2] << 32));
+    }
+    __syncthreads();
+    auto load_s = [&](int i) -> float { return all_s[i]; };
+    auto load_i = [&](int i) -> int64_t { return all_i[i]; };
+    n_sel = block_select<int64_t>(load_s, load_i, n, k, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar);
+  } else {
+    auto load_s = [&](int i) -> float { return __uint_as_float((uint32_t)ll_wait_word(entry(i), epoch)); };
+    auto load_i = [&](int i) -> int64_t {
+      const uint64_t* e = entry(i);
+      uint64_t lo = ll_wait_word(e + 1, epoch), hi = ll_wait_word(e + 2, epoch);
+      return (int64_t)((lo & 0xffffffffull) | (hi << 32));
+    };
+    n_sel = block_select<int64_t>(load_s, load_i, n, k, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar);
+  }
   __syncthreads();
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     bool ok = j < n_sel && sel_i[j] >= 0;
@@ -397,20 +439,32 @@ int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap,
   return VODB_OK;
 }
 
+// dynamic shared memory of the merge kernels: selection buffers [P] + (if it fits) the staged world*k entries
+static size_t merge_smem(int P, int n, int* staged) {
+  const size_t sel = ((size_t)P * (sizeof(int64_t) + sizeof(uint32_t)) + 15) & ~(size_t)15;
+  const size_t all = (size_t)n * (sizeof(int64_t) + sizeof(float));
+  *staged = (sel + all <= 190 * 1024) ? 1 : 0;
+  return *staged ? sel + all : sel;
+}
+
 int launch_merge_exchange(const uint64_t* gather_ll, uint32_t epoch, int world, size_t slot_words, size_t flag_word, int nq,
                           int k, float* out_s, int64_t* out_i, int* overflow_any, cudaStream_t stream) {
-  int P = pow2ceil(k);
-  size_t smem = (size_t)P * (sizeof(int64_t) + sizeof(uint32_t));
-  VODB_CUDA_CHECK(launch_pdl(merge_exchange_kernel, dim3(nq), dim3(kSelThreads), smem, stream, gather_ll, epoch, world,
-                             slot_words, flag_word, nq, k, P, out_s, out_i, overflow_any));
+  int P = pow2ceil(k), staged = 0;
+  const size_t smem = merge_smem(P, world * k, &staged);
+  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&merge_exchange_kernel), smem));
+  const int threads = (nq <= 512) ? 1024 : kSelThreads;
+  VODB_CUDA_CHECK(launch_pdl(merge_exchange_kernel, dim3(nq), dim3(threads), smem, stream, gather_ll, epoch, world,
+                             slot_words, flag_word, nq, k, P, staged, out_s, out_i, overflow_any));
   return VODB_OK;
 }
 
 int launch_merge(const float* scores, const int64_t* idx, int n_lists, int nq, int k_in, int k_out, float* out_s,
                  int64_t* out_i, cudaStream_t stream) {
-  int P = pow2ceil(k_out);
-  size_t smem = (size_t)P * (sizeof(int64_t) + sizeof(uint32_t));
-  merge_kernel<<<nq, kSelThreads, smem, stream>>>(scores, idx, n_lists, nq, k_in, k_out, P, out_s, out_i);
+  int P = pow2ceil(k_out), staged = 0;
+  const size_t smem = merge_smem(P, n_lists * k_in, &staged);
+  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&merge_kernel), smem));
+  const int threads = (nq <= 512) ? 1024 : kSelThreads;
+  merge_kernel<<<nq, threads, smem, stream>>>(scores, idx, n_lists, nq, k_in, k_out, P, staged, out_s, out_i);
   VODB_CUDA_CHECK(cudaGetLastError());
   return VODB_OK;
 }

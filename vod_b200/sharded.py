@@ -272,6 +272,7 @@ class MultiGpuStore:
         self.stores = [CorpusStore(hi - lo, dim, dtype=dtype, device=d, row_offset=lo)
                        for d, (lo, hi) in zip(self.devices, self.bounds)]
         self.device = self.devices[0]
+        self._bufs: dict = {}
 
     @property
     def ntotal(self) -> int:
@@ -294,7 +295,36 @@ class MultiGpuStore:
         for st, (lo, hi) in zip(self.stores, self.bounds):
             st.fill_synthetic(seed, 0, hi - lo, unit_norm=unit_norm)
 
+    def _buffers(self, B: int, k: int):
+        """Per-(B, k) work buffers, allocated once: queries on every device, each device's [B,k] result, the gathered
+        [G,B,k] lists and the merged result on the first device, and the pinned host mirror of the merged result."""
+        import torch
+
+        key = (B, k)
+        buf = self._bufs.get(key)
+        if buf is None:
+            if len(self._bufs) > 8:
+                self._bufs.clear()
+            dev0 = torch.device(f"cuda:{self.device}")
+            live = [st for st in self.stores if st.ntotal]
+            buf = {
+                "q": [torch.empty((B, self.dim), dtype=torch.float32, device=f"cuda:{st.device}") for st in live],
+                "out": [(torch.empty((B, k), dtype=torch.float32, device=f"cuda:{st.device}"),
+                         torch.empty((B, k), dtype=torch.int64, device=f"cuda:{st.device}")) for st in live],
+                "all_s": torch.empty((len(live), B, k), dtype=torch.float32, device=dev0),
+                "all_i": torch.empty((len(live), B, k), dtype=torch.int64, device=dev0),
+                "host_s": torch.empty((B, k), dtype=torch.float32).pin_memory(),
+                "host_i": torch.empty((B, k), dtype=torch.int64).pin_memory(),
+                "done": [torch.cuda.Event() for _ in live],
+            }
+            self._bufs[key] = buf
+        return buf
+
     def search(self, vectors: np.ndarray, top_k: int, mode: str | int | None = None) -> tuple[np.ndarray, np.ndarray]:
+        """Host queries in, merged host results out. Everything is enqueued first — H2D of the queries and the local
+        scan on every device (they run concurrently), peer copies of the [B,k] lists into the first device's gather
+        buffer (ordered by events, no host wait), the merge kernel, one D2H into pinned memory — and the host waits
+        once, at the end."""
         import torch
 
         from .search import merge_topk_device
@@ -304,35 +334,40 @@ class MultiGpuStore:
             raise ValueError(f"Expected 2D array, got {q.ndim}D array")
         if q.shape[1] != self.dim:
             raise ValueError(f"query dimension {q.shape[1]} != index dimension {self.dim}")
-        if q.dtype not in (np.float32, np.float16):
+        if q.dtype != np.float32:
             q = q.astype(np.float32)
-        for safe_pass in (False, True):
-            parts = []
-            q_host = torch.from_numpy(q)
-            for st in self.stores:  # enqueue everything first: the G scans overlap
-                if st.ntotal == 0:
-                    continue
-                with torch.cuda.device(st.device):
-                    qd = q_host.to(f"cuda:{st.device}", non_blocking=True)
-                    if safe_pass:
-                        s_np, i_np = st.search(q, top_k, mode=mode)  # synchronous entry point: overflow-proof fallback inside
-                        parts.append((torch.from_numpy(s_np).to(f"cuda:{self.device}"), torch.from_numpy(i_np).to(f"cuda:{self.device}")))
-                    else:
-                        parts.append(st.search_device(qd, top_k, mode=mode))
-            dev0 = torch.device(f"cuda:{self.device}")
-            with torch.cuda.device(dev0):
-                for st in self.stores:  # device 0 must see the other devices' results
-                    if st.device != self.device:
-                        torch.cuda.current_stream(dev0).wait_stream(torch.cuda.current_stream(st.device))
-                all_s = torch.stack([s.to(dev0, non_blocking=True) for s, _ in parts])
-                all_i = torch.stack([i.to(dev0, non_blocking=True) for _, i in parts])
-                ms, mi = merge_topk_device(all_s, all_i, top_k)
-                out = ms.cpu().numpy(), mi.cpu().numpy()
-            # read (and clear) EVERY store's sticky flag: a short-circuit would leave stale flags for the next search
-            flags = [st.check_async() for st in self.stores if st.ntotal]
-            if safe_pass or not any(flags):
-                return out
-        raise AssertionError("unreachable")
+        B = q.shape[0]
+        live = [st for st in self.stores if st.ntotal]
+        buf = self._buffers(B, int(top_k))
+        q_host = torch.from_numpy(q)
+        dev0 = torch.device(f"cuda:{self.device}")
+        for g, st in enumerate(live):  # enqueue everything first: the G scans overlap
+            with torch.cuda.device(st.device):
+                buf["q"][g].copy_(q_host, non_blocking=True)
+                st.search_device(buf["q"][g], top_k, mode=mode, out=buf["out"][g])
+                buf["done"][g].record()
+        with torch.cuda.device(dev0):
+            stream0 = torch.cuda.current_stream(dev0)
+            for g in range(len(live)):
+                stream0.wait_event(buf["done"][g])
+                buf["all_s"][g].copy_(buf["out"][g][0], non_blocking=True)   # peer copy over NVLink
+                buf["all_i"][g].copy_(buf["out"][g][1], non_blocking=True)
+            ms, mi = merge_topk_device(buf["all_s"], buf["all_i"], top_k)
+            buf["host_s"].copy_(ms, non_blocking=True)
+            buf["host_i"].copy_(mi, non_blocking=True)
+            stream0.synchronize()
+        # read (and clear) EVERY store's sticky flag: a short-circuit would leave stale flags for the next search
+        flags = [st.check_async() for st in live]
+        if not any(flags):
+            return buf["host_s"].numpy().copy(), buf["host_i"].numpy().copy()
+        # rare: a list overflowed somewhere -> every shard again through the synchronous entry point, which falls
+        # back to the overflow-proof schedule by itself
+        parts = [st.search(q, top_k, mode=mode) for st in live]
+        with torch.cuda.device(dev0):
+            all_s = torch.stack([torch.from_numpy(s) for s, _ in parts]).to(dev0)
+            all_i = torch.stack([torch.from_numpy(i) for _, i in parts]).to(dev0)
+            ms, mi = merge_topk_device(all_s, all_i, top_k)
+            return ms.cpu().numpy(), mi.cpu().numpy()
 
     def stats(self) -> dict[str, int]:
         return self.stores[0].stats()
