@@ -510,3 +510,78 @@ def test_client_accepts_cuda_tensors():
             assert out.scores.flags.writeable and isinstance(out.scores, np.ndarray)
         with pytest.raises(ValueError):
             client.search(vector=torch.zeros(128).cuda(), top_k=3)
+
+
+@pytest.mark.parametrize("mode", ["tensor", "tensor3"])
+def test_every_query_tile_width_is_bit_exact(mode):
+    """The MMA width follows the item's query count (multiples of 32) and multi-term batches run on CTA pairs
+    (<64,T> up to 64 queries, <128,T> above, the wide one-term kernel when the correction terms are empty): every
+    tile width, the last tile of multi-tile batches, and both sides of each kernel switch, against the oracle."""
+    rng = np.random.default_rng(17)
+    n, d, k = 9_000, 192, 50     # > 2 x 4096 rows: dump segment + filtered segments; odd number of 256-row pair tiles
+    xb = int_valued(rng, (n, d))
+    st = _store(xb, "bfloat16")
+    for nq in (1, 31, 32, 33, 63, 64, 65, 96, 97, 127, 128, 129, 160, 191, 193, 224, 255, 256, 257, 288, 300, 383, 385,
+               511, 513, 700):
+        xq = int_valued(rng, (nq, d))
+        if mode == "tensor3":
+            # 18 significant bits per element: needs all three bf16 terms. Only 16 nonzero dimensions per query, so every
+            # partial sum is a multiple of 2^-16 below 2^8 and float32 accumulation stays exact in any order.
+            xq = xq + int_valued(rng, (nq, d)) / 65536.0
+            keep = np.zeros((nq, d), bool)
+            for r in range(nq):
+                keep[r, rng.choice(d, size=16, replace=False)] = True
+            xq = np.where(keep, xq, 0.0).astype(np.float32)
+        s, i = st.search(xq, k, mode=mode)
+        rs, ri = flat_ip.search(xb, xq, k)
+        assert np.array_equal(i, ri), (mode, nq)
+        assert np.array_equal(s, rs), (mode, nq)
+        if mode == "tensor3" and nq in (64, 128, 300):   # correction terms empty: the one-term launch takes the batch
+            xq0 = int_valued(rng, (nq, d))
+            s, i = st.search(xq0, k, mode=mode)
+            rs, ri = flat_ip.search(xb, xq0, k)
+            assert np.array_equal(i, ri) and np.array_equal(s, rs), (mode, nq, "empty terms")
+    st.close()
+
+
+def test_auto_mode_serves_a_float32_store_from_the_tensor_cores():
+    """`auto` on a float32 store = three bf16 planes x three query terms (fp32-exact tolerance), planes built by
+    `prepare_tensor` on first use; `exact` stays available as the CUDA-core cross-check."""
+    rng = np.random.default_rng(23)
+    xb = rng.standard_normal((50_000, 256), dtype=np.float32)
+    xq = rng.standard_normal((40, 256), dtype=np.float32)
+    st = _store(xb, "float32")
+    assert st._planes_fit is None
+    s, i = st.search(xq, 100)                       # auto
+    assert st._planes_fit is True and st._mode(None, 0) == vod_b200._lib.MODE_TENSOR_X3
+    rs, ri = flat_ip.search(xb, xq, 100)
+    rep = flat_ip.compare_topk(xb, xq, s, i, rs, ri, rtol=RTOL)
+    assert rep["ok"], rep
+    s2, i2 = st.search(xq, 100, mode="exact")
+    rep2 = flat_ip.compare_topk(xb, xq, s2, i2, rs, ri, rtol=RTOL)
+    assert rep2["ok"], rep2
+    st.close()
+
+
+def test_index_built_from_a_zarr_store_on_disk(tmp_path):
+    """The reference's predict step leaves embeddings in a zarr-v2 store (ts_factory.py:54-90); `open_vectors` reads
+    it lazily and `build_b200_index` / `ingest` stream it into HBM in blocks."""
+    rng = np.random.default_rng(29)
+    xb = int_valued(rng, (2_345, 96))
+    path = vod_b200.write_zarr_v2(tmp_path / "vectors", xb, chunk_size=100)
+    vectors = vod_b200.open_vectors(path)
+    xq = int_valued(rng, (9, 96))
+    rs, ri = flat_ip.search(xb, xq, 20)
+    with vod_b200.B200SearchMaster(vectors, dtype="bfloat16", add_batch_size=700, serve=False) as master:
+        out = master.get_client().search(vector=xq, top_k=20)
+        assert np.array_equal(out.indices, ri) and np.array_equal(out.scores, rs)
+    from vod_b200 import zarr_io
+
+    st = vod_b200.CorpusStore(len(xb), 96, dtype="float16")
+    assert zarr_io.ingest(st, vectors, batch_rows=512) == len(xb)
+    s, i = st.search(xq, 20, mode="tensor")
+    assert np.array_equal(i, ri) and np.array_equal(s, rs)
+    with pytest.raises(vod_b200.VodbError):          # append-only: a block that would leave a gap is refused
+        st2 = vod_b200.CorpusStore(100, 96, dtype="float16")
+        st2.add(xb[:10], row0=50)
+    st.close()

@@ -104,6 +104,52 @@ def test_concurrent_requests_share_scans():
 
 
 @pytest.mark.timeout(60)
+def test_shared_scans_are_cut_at_query_tile_multiples():
+    """Cost model of the coalescer: a scan costs one corpus pass per `quantum` queries, so when more than one tile
+    is waiting the batch stops at the last request that fits a multiple of the tile; nobody is dropped or reordered."""
+    import threading
+    import time
+
+    from vod_b200.transport import ScanCoalescer
+
+    gate = threading.Event()
+    widths = []
+
+    def search(vectors, top_k, mode):
+        widths.append(len(vectors))
+        if len(widths) == 1:
+            gate.wait(5)            # hold the first scan until the other requests have queued up
+        return _fake_search(vectors, top_k, mode)
+
+    co = ScanCoalescer(search, max_queries=1024, quantum=128)
+    out = {}
+
+    def caller(t):
+        v = np.full((32, 8), float(t), np.float32)
+        out[t] = (v, co.submit(v, 4, None))
+
+    first = threading.Thread(target=caller, args=(0,))
+    first.start()
+    while not widths:
+        time.sleep(0.005)
+    rest = [threading.Thread(target=caller, args=(t,)) for t in range(1, 6)]   # 5 x 32 = 160 queries wait
+    for th in rest:
+        th.start()
+        time.sleep(0.01)            # deterministic arrival order
+    while len(co._pending) < 5:
+        time.sleep(0.005)
+    gate.set()
+    for th in [first, *rest]:
+        th.join()
+    co.close()
+    assert widths == [32, 128, 32], widths   # 160 waiting -> one full tile now, the remaining request next
+    assert [n for n, _, _ in co.scan_log] == widths and all(ms >= 0 for _, _, ms in co.scan_log)
+    for t, (v, (s, i)) in out.items():
+        exp_s, exp_i = _fake_search(v, 4, None)
+        assert np.array_equal(s, exp_s) and np.array_equal(i, exp_i)
+
+
+@pytest.mark.timeout(60)
 def test_failed_scan_reaches_every_waiter_and_server_keeps_running():
     from vod_b200.transport import ScanCoalescer
 

@@ -160,8 +160,24 @@ struct TcParams {
   // a block the QUERY tile is the slow index: during the first pass every CTA streams a different corpus tile from
   // HBM (each line is requested once), the remaining n_qtiles - 1 passes find the block in L2.
   int raster_tiles;
+  // The last query tile of a one-term batch is staged through its own tensor map whose box is only as tall as the
+  // tile's MMA width (item_columns): a batch of 160 queries moves 160, not 256, query rows per K chunk over the
+  // L2 -> SM path, which is the path that limits these kernels. Bytes of that box (per CTA, per term).
+  uint32_t last_box_bytes;
 };
 constexpr int kTermAlways = 0, kOnlyIfSingleTerm = 1, kOnlyIfMultiTerm = 2;
+
+// MMA N of an item = its query columns rounded up to 32 (not the full tile): the last query tile of a batch costs
+// tensor-pipe time in proportion to the queries it holds. 32 because the epilogue reads the accumulator 32 columns
+// at a time and must only see columns this item's MMAs wrote (the staged query rows up to the tile end are zero, so
+// those columns hold 0 and fail against tau = +inf; never-written TMEM could hold a +inf bit pattern).
+__device__ __forceinline__ int item_columns(const TcParams& p, int q0, int bn) {
+  const int rem = p.nq - q0;
+  return rem >= bn ? bn : ((rem + 31) & ~31);
+}
+__device__ __forceinline__ uint32_t idesc_with_n(uint32_t idesc, int n) {
+  return (idesc & ~(0x3fu << 17)) | ((uint32_t)(n >> 3) << 17);
+}
 
 __device__ __forceinline__ void item_to_tiles(const TcParams& p, int item, int& ct, int& qt) {
   if (p.raster_tiles <= 0) {
@@ -283,24 +299,30 @@ __device__ __forceinline__ void epilogue_begin_item(const TcParams& p, WarpStage
 // the others the corrections, which are summed first and added to the leading product last
 // `groups` (<= GROUPS, uniform over the CTA) is how many of them this launch actually wrote: correction terms that are
 // zero for the whole query batch are skipped by the producer and the MMA warp, and their columns hold nothing.
-template <int BN, int GROUPS = 1>
+// HALF > 0 (CTA-pair kernels with the terms stacked in one MMA): the accumulator holds, for each CTA's half of the
+// item's queries (HALF = BN/2 of them), `groups` column groups HALF apart — [half h][term t][query j] — instead of
+// `groups` groups BN apart.
+template <int BN, int GROUPS = 1, int HALF = 0>
 __device__ __forceinline__ void epilogue_columns(const TcParams& p, WarpStage& ws, const float* tau_cur,
-                                                 uint32_t taddr0, int64_t row, bool valid, int q0, int sb, int groups) {
+                                                 uint32_t taddr0, int64_t row, bool valid, int q0, int sb, int groups,
+                                                 int n_cols = BN) {
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = 0; c0 < n_cols; c0 += 32) {
     uint32_t v[32];
-    tmem_ld_32x32b_x32(taddr0 + (uint32_t)c0, v);
+    const int gs = HALF > 0 ? HALF : BN;                                                   // distance between groups
+    const int cb = HALF > 0 ? (c0 / HALF) * (groups * HALF) + (c0 % HALF) : c0;             // column of the leading group
+    tmem_ld_32x32b_x32(taddr0 + (uint32_t)cb, v);
     if (GROUPS >= 3 && groups >= 3) {
       uint32_t w[32], x[32];
-      tmem_ld_32x32b_x32(taddr0 + (uint32_t)(BN + c0), w);
-      tmem_ld_32x32b_x32(taddr0 + (uint32_t)(2 * BN + c0), x);
+      tmem_ld_32x32b_x32(taddr0 + (uint32_t)(cb + gs), w);
+      tmem_ld_32x32b_x32(taddr0 + (uint32_t)(cb + 2 * gs), x);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __fadd_rn(__uint_as_float(w[j]), __uint_as_float(x[j]))));
     } else if (GROUPS >= 2 && groups >= 2) {
       uint32_t w[32];
-      tmem_ld_32x32b_x32(taddr0 + (uint32_t)(BN + c0), w);
+      tmem_ld_32x32b_x32(taddr0 + (uint32_t)(cb + gs), w);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(w[j])));
@@ -398,7 +420,7 @@ struct TcConfig {
 template <int BN, int T, int P = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_constant__ CUtensorMap tmap_query,
-                const TcParams p) {
+                const __grid_constant__ CUtensorMap tmap_query_last, const TcParams p) {
   using Cfg = TcConfig<BN, T, P>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ unsigned char smem_raw[];
@@ -463,6 +485,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       // ---------------- TMA producer ----------------
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_corpus) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_query) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_query_last) : "memory");
       const uint64_t corpus_policy = (p.n_qtiles == 1) ? kEvictFirst : kEvictLast;
       int stage = 0;
       uint32_t phase = 0;
@@ -471,12 +494,15 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
         item_to_tiles(p, item, ct, qt);
         const int row0 = (int)(p.row_begin + (int64_t)ct * BM);
         const int q0 = qt * BN;
+        const bool last_q = (T == 1 && P == 1 && qt == p.n_qtiles - 1);  // narrower box for the last query tile
+        const CUtensorMap* qmap = last_q ? &tmap_query_last : &tmap_query;
+        const uint32_t b_bytes = last_q ? p.last_box_bytes : Cfg::kBBytes;
         for (int kc = 0; kc < p.kchunks; ++kc) {
 #pragma unroll
           for (int pl = 0; pl < P; ++pl) {
             const int nt = (P == 1) ? nt_run : (P - pl);  // query terms multiplied with this plane
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], Cfg::kABytes + (uint32_t)nt * Cfg::kBBytes);
+            mbar_expect_tx(&full_bar[stage], Cfg::kABytes + (uint32_t)nt * b_bytes);
             // blocked order: the last pass over a block lets its lines go (the next block needs the room)
             tma_load_2d(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC,
                         pl * p.plane_rows + row0,
@@ -484,7 +510,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
 #pragma unroll
             for (int t = 0; t < T; ++t)
               if (t < nt)
-                tma_load_2d(&tmap_query, &full_bar[stage], smem_b + (stage * T + t) * Cfg::kBBytes, kc * KC,
+                tma_load_2d(qmap, &full_bar[stage], smem_b + (stage * T + t) * Cfg::kBBytes, kc * KC,
                             t * p.q_rows_pad + q0, kEvictLast);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -500,6 +526,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
+        uint32_t idesc_item = p.idesc;
+        if constexpr (T == 1 && P == 1) {  // one term: the MMA is as wide as the item's queries (multiple of 32)
+          int ct, qt;
+          item_to_tiles(p, item, ct, qt);
+          idesc_item = idesc_with_n(p.idesc, item_columns(p, qt * BN, BN));
+        }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * Cfg::kAccCols;  // leading product; corrections at + BN
@@ -531,7 +563,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
                   const bool lead = (pl == 0 && t == 0);
                   const bool first = (kc | k) == 0 && (lead || (pl == 0 && t == 1));  // first MMA into its accumulator
                   umma_f16(lead || !Cfg::kDual ? tmem_d : tmem_d + (uint32_t)BN, da + (uint64_t)(2 * k),
-                           db + (uint64_t)(2 * k), p.idesc, first ? 0u : 1u);
+                           db + (uint64_t)(2 * k), idesc_item, first ? 0u : 1u);
                 }
               }
             }
@@ -568,7 +600,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_co
       tcgen05_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * Cfg::kAccCols;
       epilogue_columns<BN, Cfg::kGroups>(p, ws, tau_cur, taddr0, row, valid, q0, sb,
-                                          P == 1 ? (Cfg::kConcat ? nt_run : (nt_run > 1 ? 2 : 1)) : Cfg::kGroups);
+                                          P == 1 ? (Cfg::kConcat ? nt_run : (nt_run > 1 ? 2 : 1)) : Cfg::kGroups,
+                                          (T == 1 && P == 1) ? item_columns(p, q0, BN) : BN);
       // all TMEM reads of this buffer are complete (wait::ld above): hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
@@ -654,26 +687,43 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
       : "memory");
 }
 
+constexpr uint32_t kSmemMax = 227 * 1024;  // dynamic shared memory one CTA may opt into on sm_100
+
+// BN = queries per pair item, T = query terms (see TcConfig). Each CTA stages its own 128 corpus rows and, per term,
+// its own half (BN/2) of the item's queries: kABytes + T * kBBytes per stage against kABytes + T * 2 * kBBytes in the
+// 1-CTA kernel for the same MMA work per SM, i.e. more stages in flight (7 instead of 5 at <64,3>, 5 instead of 3 at
+// <128,3>) and half the query bytes per SM on the L2 -> SM path. Stacked terms (T * BN <= 256): ONE MMA of N = nt * BN per
+// K step; CTA h's B tile holds [term][query of half h], so the accumulator columns are [half][term][query] (epilogue
+// HALF = BN/2). Otherwise (<128,3>): one MMA of N = BN per term, leading product and corrections in two accumulators.
+template <int BN, int T>
 struct Tc2Config {
-  static constexpr int BN = 256;                       // queries per pair item (MMA N)
-  static constexpr uint32_t kABytes = BM * KC * 2;     // this CTA's 128 corpus rows
-  static constexpr uint32_t kBBytes = (BN / 2) * KC * 2;  // this CTA's 128 queries
-  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 6;
-  static constexpr uint32_t kTmemCols = 512;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256 + 4 * BN * sizeof(float) + 4 * sizeof(WarpStage);
+  static constexpr uint32_t kABytes = BM * KC * 2;          // this CTA's 128 corpus rows
+  static constexpr uint32_t kBBytes = (BN / 2) * KC * 2;    // one term, this CTA's half of the item's queries
+  static constexpr uint32_t kStageBytes = kABytes + T * kBBytes;
+  static constexpr uint32_t kExtra = 1024 + 256 + 4 * BN * sizeof(float) + 4 * sizeof(WarpStage);
+  static constexpr int kFit = (kSmemMax - kExtra) / kStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;
+  static constexpr bool kConcat = (T > 1) && (T * BN <= 256);
+  static constexpr bool kDual = (T > 1) && !kConcat;
+  static constexpr int kGroups = kConcat ? T : (kDual ? 2 : 1);
+  static constexpr int kHalf = kConcat ? BN / 2 : 0;
+  static constexpr uint32_t kAccCols = kGroups * BN;
+  static_assert(2 * kAccCols <= 512, "two accumulator buffers must fit the 512 TMEM columns");
+  static constexpr uint32_t kTmemCols = (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128 : (2 * kAccCols <= 256) ? 256 : 512;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kExtra;
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 
+template <int BN, int T>
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_constant__ CUtensorMap tmap_query,
-                 const TcParams p) {
-  using Cfg = Tc2Config;
+                 const __grid_constant__ CUtensorMap tmap_query_last, const TcParams p) {
+  using Cfg = Tc2Config<BN, T>;
   constexpr int STAGES = Cfg::kStages;
-  constexpr int BN = Cfg::BN;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_a = smem;
-  unsigned char* smem_b = smem + STAGES * Cfg::kABytes;
+  unsigned char* smem_b = smem + STAGES * Cfg::kABytes;   // STAGES x T x [BN/2 x 128B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -717,10 +767,16 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
   const int n_pairs = gridDim.x >> 1;
   const int pair = blockIdx.x >> 1;
   int n_items = p.n_ctiles * p.n_qtiles;  // n_ctiles counts 256-row pair tiles here
-  if (p.term_policy == kOnlyIfSingleTerm) {   // uniform over the grid: every CTA reads the same masks
+  // which query terms carry anything (prepare kernel's masks; the same answer in every CTA of the grid)
+  int nt_run = T;
+  if (T > 1 || p.term_policy != kTermAlways) {
     int m = 0;
     for (int i = threadIdx.x; i < p.term_blocks; i += kThreads) m |= p.term_any[i];
-    if (__syncthreads_or(m & 2)) n_items = 0;  // correction terms present: the multi-term kernel has this batch
+    const int any1 = __syncthreads_or(m & 2), any2 = __syncthreads_or(m & 4);
+    const int nt_needed = any2 ? 3 : any1 ? 2 : 1;
+    if (T > 1) nt_run = nt_needed < T ? nt_needed : T;
+    if (p.term_policy == kOnlyIfSingleTerm && nt_needed > 1) n_items = 0;  // the multi-term launch has this batch
+    if (p.term_policy == kOnlyIfMultiTerm && nt_needed == 1) n_items = 0;  // the one-term launch has this batch
   }
 
   if (warp == 0) {
@@ -728,19 +784,31 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
       // ---------------- TMA producer (both CTAs) ----------------
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_corpus) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_query) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_query_last) : "memory");
       int stage = 0;
       uint32_t phase = 0;
       for (int item = pair; item < n_items; item += n_pairs) {
         int ct, qt;
         item_to_tiles(p, item, ct, qt);
         const int row0 = (int)(p.row_begin + ((int64_t)ct * 2 + rank) * BM);
-        const int q0 = qt * BN + (int)rank * (BN / 2);
+        // this CTA supplies half of the item's query columns: rows [rank * n/2, (rank + 1) * n/2) of the tile (the box is
+        // always BN/2 rows; the MMA reads the first n/2 of them). Only one-term items are narrower than BN.
+        const int n_item = (T == 1) ? item_columns(p, qt * BN, BN) : BN;
+        const int q0 = qt * BN + (int)rank * (n_item / 2);
+        const uint64_t corpus_policy =
+            (p.n_qtiles == 1 || (p.raster_tiles > 0 && qt == p.n_qtiles - 1)) ? kEvictFirst : kEvictLast;
+        const bool last_q = (T == 1 && qt == p.n_qtiles - 1);  // narrower box for the last query tile
+        const CUtensorMap* qmap = last_q ? &tmap_query_last : &tmap_query;
+        const uint32_t b_bytes = last_q ? p.last_box_bytes : Cfg::kBBytes;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-          tma_load_2d_2sm(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC, row0,
-                          (p.n_qtiles == 1 || (p.raster_tiles > 0 && qt == p.n_qtiles - 1)) ? kEvictFirst : kEvictLast);
-          tma_load_2d_2sm(&tmap_query, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kc * KC, q0, kEvictLast);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + (uint32_t)nt_run * b_bytes));
+          tma_load_2d_2sm(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC, row0, corpus_policy);
+#pragma unroll
+          for (int t = 0; t < T; ++t)
+            if (t < nt_run)
+              tma_load_2d_2sm(qmap, &full_bar[stage], smem_b + (stage * T + t) * Cfg::kBBytes, kc * KC,
+                              t * p.q_rows_pad + q0, kEvictLast);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -754,17 +822,36 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
       for (int item = pair; item < n_items; item += n_pairs, ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
+        int ct, qt;
+        item_to_tiles(p, item, ct, qt);
+        // MMA N: one term -> the item's query columns; stacked terms -> nt * BN; one MMA per term -> BN
+        const uint32_t idesc_item =
+            idesc_with_n(p.idesc, T == 1 ? item_columns(p, qt * BN, BN) : (Cfg::kConcat ? nt_run * BN : BN));
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * Cfg::kAccCols;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t db = make_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+          if constexpr (!Cfg::kDual) {
+            const uint64_t db = make_desc_sw128(smem_u32(smem_b + (stage * T) * Cfg::kBBytes));
 #pragma unroll
-          for (int k = 0; k < KC / UMMA_K; ++k)
-            umma_f16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kc | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < KC / UMMA_K; ++k)
+              umma_f16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_item, (kc | k) != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              if (t >= nt_run) break;
+              const uint64_t db = make_desc_sw128(smem_u32(smem_b + (stage * T + t) * Cfg::kBBytes));
+#pragma unroll
+              for (int k = 0; k < KC / UMMA_K; ++k) {
+                const bool first = (kc | k) == 0 && t <= 1;  // first MMA into the leading / the correction accumulator
+                umma_f16_2sm(t == 0 ? tmem_d : tmem_d + (uint32_t)BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k),
+                             idesc_item, first ? 0u : 1u);
+              }
+            }
+          }
           umma_commit_2sm(&empty_bar[stage]);  // frees the stage in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -795,8 +882,10 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_columns<BN>(p, ws, tau_cur, taddr0, row, valid, q0, sb, 1);
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * Cfg::kAccCols;
+      epilogue_columns<BN, Cfg::kGroups, Cfg::kHalf>(p, ws, tau_cur, taddr0, row, valid, q0, sb,
+                                                      Cfg::kConcat ? nt_run : (nt_run > 1 ? 2 : 1),
+                                                      T == 1 ? item_columns(p, q0, BN) : BN);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cta(&tempty_bar[acc], 0);  // the leader's barrier collects both CTAs' epilogues
@@ -870,11 +959,6 @@ bool raster_enabled() {
   return env ? (env[0] != '0') : true;
 }
 bool use_pair_kernel(const SegmentArgs& a) { return pair_kernel_enabled() && a.terms == 1 && a.planes == 1 && a.nq > 128; }
-// large multi-term batches on a 16-bit store: the pair kernel also runs, for the case that the correction terms
-// turn out empty on the device (see TcParams::term_policy)
-bool use_pair_kernel_for_single_term(const SegmentArgs& a) {
-  return pair_kernel_enabled() && a.terms > 1 && a.planes == 1 && a.nq > 128;
-}
 
 // corpus tensor map (cached in the store): the rows themselves (bf16 / fp16 store), or the bf16 planes of an fp32
 // store stacked along the rows ([3 * n_rows, pitch]; plane p of row r is row p * n_rows + r)
@@ -905,8 +989,14 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   const int64_t q_rows_pad = ((int64_t)a.nq + 255) / 256 * 256;
   rc = encode_2d(&tmap_q, a.queries, a.dtype, q_rows_pad * T, s->pitch, BN);
   if (rc != VODB_OK) return rc;
+  // the last query tile's own box: as tall as its MMA is wide (multiple of 32 rows)
+  alignas(64) CUtensorMap tmap_q_last;
+  const int last_cols = std::min(BN, ((a.nq - ((a.nq - 1) / BN) * BN) + 31) / 32 * 32);
+  rc = encode_2d(&tmap_q_last, a.queries, a.dtype, q_rows_pad * T, s->pitch, last_cols);
+  if (rc != VODB_OK) return rc;
 
   TcParams p;
+  p.last_box_bytes = (uint32_t)last_cols * KC * 2;
   p.row_begin = a.row_begin;
   p.row_end = a.row_end;
   p.nq = a.nq;
@@ -924,7 +1014,7 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.dump = a.dump ? 1 : 0;
   p.term_any = a.term_any;
   p.term_blocks = a.term_blocks;
-  p.term_policy = (T > 1 && P == 1 && use_pair_kernel_for_single_term(a)) ? kOnlyIfMultiTerm : kTermAlways;
+  p.term_policy = kTermAlways;
   const uint32_t fmt = (a.dtype == VODB_BF16) ? 1u : 0u;  // UMMA F16F32Format: F16=0, BF16=1
   p.idesc = (1u << 4) /*D=f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
@@ -932,26 +1022,32 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   int grid = (int)(items < s->sm_count ? items : s->sm_count);
   p.raster_tiles = (p.n_qtiles > 1 && raster_enabled()) ? grid : 0;
   VODB_CUDA_CHECK(launch_pdl(score_tc_kernel<BN, T, P>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream,
-                             *tmap_store, tmap_q, p));
+                             *tmap_store, tmap_q, tmap_q_last, p));
   return VODB_OK;
 }
 
-int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
-  using Cfg = Tc2Config;
-  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&score_tc2_kernel), Cfg::kSmemBytes));
+template <int BN, int T>
+int launch_pair(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream_t stream) {
+  using Cfg = Tc2Config<BN, T>;
+  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&score_tc2_kernel<BN, T>), Cfg::kSmemBytes));
   const CUtensorMap* tmap_store = nullptr;
   int rc = corpus_tensor_map(s, &tmap_store);
   if (rc != VODB_OK) return rc;
   alignas(64) CUtensorMap tmap_q;
   const int64_t q_rows_pad = ((int64_t)a.nq + 255) / 256 * 256;
-  rc = encode_2d(&tmap_q, a.queries, a.dtype, q_rows_pad, s->pitch, Cfg::BN / 2);
+  rc = encode_2d(&tmap_q, a.queries, a.dtype, q_rows_pad * T, s->pitch, BN / 2);  // box = one CTA's half of a query tile
+  if (rc != VODB_OK) return rc;
+  alignas(64) CUtensorMap tmap_q_last;  // the last query tile's own box: half of its MMA width
+  const int last_cols = std::min(BN, ((a.nq - ((a.nq - 1) / BN) * BN) + 31) / 32 * 32);
+  rc = encode_2d(&tmap_q_last, a.queries, a.dtype, q_rows_pad * T, s->pitch, last_cols / 2);
   if (rc != VODB_OK) return rc;
   TcParams p;
+  p.last_box_bytes = (uint32_t)(last_cols / 2) * KC * 2;
   p.row_begin = a.row_begin;
   p.row_end = a.row_end;
   p.nq = a.nq;
   p.n_ctiles = (int)((a.row_end - a.row_begin + 2 * BM - 1) / (2 * BM));  // 256-row pair tiles
-  p.n_qtiles = (a.nq + Cfg::BN - 1) / Cfg::BN;
+  p.n_qtiles = (a.nq + BN - 1) / BN;
   p.kchunks = (s->dim + KC - 1) / KC;  // the pitch may carry one more, unscanned chunk (api.cu vodb_store_create)
   p.q_rows_pad = (int)q_rows_pad;
   p.plane_rows = 0;
@@ -964,9 +1060,9 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   p.dump = a.dump ? 1 : 0;
   p.term_any = a.term_any;
   p.term_blocks = a.term_blocks;
-  p.term_policy = (a.terms > 1) ? kOnlyIfSingleTerm : kTermAlways;
+  p.term_policy = term_policy;
   const uint32_t fmt = (a.dtype == VODB_BF16) ? 1u : 0u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cfg::BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
   int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
   if (items <= 0) return VODB_OK;
   int pairs = (int)std::min<int64_t>(items, s->sm_count / 2);
@@ -985,8 +1081,20 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  VODB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, score_tc2_kernel, *tmap_store, tmap_q, p));
+  VODB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, score_tc2_kernel<BN, T>, *tmap_store, tmap_q, tmap_q_last, p));
   return VODB_OK;
+}
+
+// multi-term scan of a 16-bit store on CTA pairs. Batches above 128 queries are launched twice — the wide one-term
+// kernel, which works only if the correction terms turn out empty on the device (float32 queries that are exact in
+// the store dtype), and the multi-term kernel, which works only if they do not: exactly one of them finds items.
+template <int T>
+int launch_pair_terms(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
+  if (a.nq <= 64) return launch_pair<64, T>(s, a, kTermAlways, stream);
+  if (a.nq <= 128) return launch_pair<128, T>(s, a, kTermAlways, stream);
+  int rc = launch_pair<256, 1>(s, a, kOnlyIfSingleTerm, stream);
+  if (rc != VODB_OK) return rc;
+  return launch_pair<128, T>(s, a, kOnlyIfMultiTerm, stream);
 }
 
 }  // namespace
@@ -1013,12 +1121,10 @@ int launch_score_tensor(vodb_store* s, const SegmentArgs& a, cudaStream_t stream
     if (a.planes == 2) return a.nq <= 64 ? launch_bn<64, 2, 2>(s, a, stream) : launch_bn<128, 2, 2>(s, a, stream);
     return a.nq <= 64 ? launch_bn<64, 3, 3>(s, a, stream) : launch_bn<128, 3, 3>(s, a, stream);
   }
-  if (use_pair_kernel(a)) return launch_pair(s, a, stream);
-  if (use_pair_kernel_for_single_term(a)) {
-    int rc = launch_pair(s, a, stream);  // works only if the correction terms are empty; the launch below otherwise
-    if (rc != VODB_OK) return rc;
-  }
-  switch (a.terms) {
+  if (use_pair_kernel(a)) return launch_pair<256, 1>(s, a, kTermAlways, stream);
+  if (pair_kernel_enabled() && a.terms == 2) return launch_pair_terms<2>(s, a, stream);
+  if (pair_kernel_enabled() && a.terms == 3) return launch_pair_terms<3>(s, a, stream);
+  switch (a.terms) {  // 1-CTA kernels: one term up to 128 queries; everything when VODB_TC2=0
     case 1:
       if (a.nq <= 64) return launch_bn<64, 1>(s, a, stream);
       if (a.nq <= 128) return launch_bn<128, 1>(s, a, stream);
