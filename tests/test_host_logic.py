@@ -142,7 +142,9 @@ def test_scan_schedule_invariants(n_rows, nq, k):
 
 def test_scan_schedule_headline_shapes():
     cap, b = _plan(10_000_000, 64, 100)
-    assert cap == 16384 and len(b) - 1 == 4 and b[1] == 4096            # BASELINE configs[1], 64 queries
+    assert cap == 65536 and len(b) - 1 == 3 and b[1] == 16384           # BASELINE configs[1], 64 queries
+    cap, b = _plan(1_250_000, 64, 100)
+    assert len(b) - 1 == 2 and b[1] == 16384                            # its 8-GPU shard: dump segment + one scan
     cap, b = _plan(10_000_000, 8192, 100)
     assert len(b) - 1 == 7
     cap, b = _plan(12_500_000, 64, 1000)

@@ -110,7 +110,7 @@ __global__ void prepare_kernel(const S* __restrict__ src, int src_dim, D* __rest
   pdl_wait();  // the previous search on this stream may still be reading the staging buffer / lists
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gtid < n) {
-    cnt[gtid] = first_rows;
+    cnt[gtid * kCntStride] = first_rows;
     tau[gtid] = -INFINITY;
   }
   // rows [n, fill_rows) are the rest of the last query tile: zero them, so that whatever an earlier call left there
@@ -345,6 +345,9 @@ int choose_cap(int nq, int k) {
   if (env_cap) return std::max(pow2ceil_host(4LL * k), pow2ceil_host(std::atoll(env_cap)));
   int64_t cap = pow2ceil_host(std::max<int64_t>(128LL * k, 8192));
   cap = std::min<int64_t>(cap, 65536);
+  // small batches: 64k slots per list (<= 134 MB in all) let the segments grow 80-fold, i.e. a 1.25M-row shard is two
+  // segments and a 10M-row shard three (one select + two launches less per search; scripts/r02_sweep_schedule2.py)
+  if (nq <= 256) cap = 65536;
   const int64_t budget = 4LL << 30;
   while (cap > 4LL * k && cap > 2048 && (int64_t)nq * cap * 8 > budget) cap >>= 1;
   cap = std::max<int64_t>(cap, pow2ceil_host(4LL * k));
@@ -382,7 +385,7 @@ int ensure_workspace(vodb_store* s, int nq, int k, int q_elem_bytes, cudaStream_
     if (w.cnt) cudaFree(w.cnt);
     if (w.tau) cudaFree(w.tau);
     w.cnt = nullptr; w.tau = nullptr;
-    VODB_CUDA_CHECK(cudaMalloc(&w.cnt, (size_t)nq * sizeof(int)));
+    VODB_CUDA_CHECK(cudaMalloc(&w.cnt, (size_t)nq * kCntStride * sizeof(int)));
     VODB_CUDA_CHECK(cudaMalloc(&w.tau, (size_t)nq * sizeof(float)));
     w.nq_cap = nq;
   }
@@ -452,7 +455,7 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
   // first segment ("dump": every score stored, then one select). Measured on B200 (scripts/sweep_schedule.py,
   // 64 queries, k=100): 1024..8192 rows and growth 8..32 are within ~1% of each other on a 10M-row shard; on a
   // 1.25M-row shard (8-GPU split) 4096/8192 rows with growth >= 20 (3 segments) beat 1024/2048 rows by ~7%.
-  int64_t first = round128(std::min<int64_t>(cap / 2, std::max<int64_t>(4096, 16LL * k)));
+  int64_t first = round128(std::min<int64_t>(cap / 2, std::max<int64_t>(large_batch ? 4096 : 16384, 16LL * k)));
   if (large_batch) first = std::min<int64_t>(first, std::max<int64_t>(4096, round128(4LL * k)));
   // tuning knobs (development): VODB_FIRST_ROWS / VODB_GROWTH override the schedule of small batches
   static const char* env_first = std::getenv("VODB_FIRST_ROWS");
@@ -467,7 +470,7 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
   }
   b.push_back(first);
   // growth: expected survivors of a segment = k * seg/before; keep that below cap/8
-  double g = std::max(1.0, std::min((double)cap / (8.0 * k), large_batch ? 3.0 : 32.0));
+  double g = std::max(1.0, std::min((double)cap / (8.0 * k), large_batch ? 3.0 : 96.0));
   if (env_growth && !large_batch) g = std::max(1.0, std::atof(env_growth));
   if (env_growth_large && large_batch) g = std::max(1.0, std::min((double)cap / (8.0 * k), std::atof(env_growth_large)));
   int64_t cur = first;
@@ -986,7 +989,7 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
       rc = run_scan(s, q_dev, q_dtype, nq, k, mode, safe_run, nullptr, nullptr, st, &xd);
     } else {
       // an empty shard (more ranks than row blocks) contributes an all-padding list
-      VODB_CUDA_CHECK(cudaMemsetAsync(w.cnt, 0, (size_t)nq * sizeof(int), st));
+      VODB_CUDA_CHECK(cudaMemsetAsync(w.cnt, 0, (size_t)nq * kCntStride * sizeof(int), st));
       rc = launch_select(w.cand_s, w.cand_i, w.cnt, w.tau, w.cap, nq, k, true, nullptr, nullptr, s->row_offset, st, &xd);
     }
     if (rc != VODB_OK) return rc;

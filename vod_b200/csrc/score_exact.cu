@@ -190,7 +190,7 @@ score_exact_kernel(const T* __restrict__ corpus, int pitch, int64_t row_begin, i
           cand_i[(size_t)q * cap + (size_t)(r - row_begin)] = (int32_t)r;
         }
       } else if (q < nq && s >= tau_s[n]) {
-        int pos = atomicAdd(&cnt[q], 1);
+        int pos = atomicAdd(&cnt[(size_t)q * kCntStride], 1);
         if (pos < cap) {
           cand_s[(size_t)q * cap + pos] = s;
           cand_i[(size_t)q * cap + pos] = (int32_t)r;

@@ -164,6 +164,7 @@ struct TcParams {
   // tile's MMA width (item_columns): a batch of 160 queries moves 160, not 256, query rows per K chunk over the
   // L2 -> SM path, which is the path that limits these kernels. Bytes of that box (per CTA, per term).
   uint32_t last_box_bytes;
+  int n_stages;  // resident-query pair kernel: depth of the corpus ring (what is left of shared memory), else unused
 };
 constexpr int kTermAlways = 0, kOnlyIfSingleTerm = 1, kOnlyIfMultiTerm = 2;
 
@@ -210,7 +211,7 @@ struct WarpStage {
 
 __device__ __noinline__ void append_global(int* cnt, float* cand_s, int32_t* cand_i, int* overflow, int cap, int q,
                                            float s, int32_t row) {
-  const int pos = atomicAdd(&cnt[q], 1);
+  const int pos = atomicAdd(&cnt[(size_t)q * kCntStride], 1);
   if (pos < cap) {
     cand_s[(size_t)q * cap + pos] = s;
     cand_i[(size_t)q * cap + pos] = row;
@@ -239,7 +240,7 @@ __device__ __forceinline__ void flush_issue(const TcParams& p, const WarpStage& 
       f.s[u] = ws.s[b][e];
       f.row[u] = ws.row[b][e];
       f.q[u] = ws.q[b][e];
-      f.pos[u] = atomicAdd(&p.cnt[f.q[u]], 1);
+      f.pos[u] = atomicAdd(&p.cnt[(size_t)f.q[u] * kCntStride], 1);
     }
   }
 }
@@ -281,13 +282,14 @@ template <int BN>
 __device__ __forceinline__ void epilogue_begin_item(const TcParams& p, WarpStage& ws, float* tau_cur, int q0, int sb,
                                                     int local, int lane, PendingFlush& pend) {
   if (!p.dump) {
-    if (local > 0) flush_issue(p, ws, sb ^ 1, lane, pend);
+    // thresholds first: their loads must not queue behind the flush's atomics in the memory pipeline
     if (q0 + BN <= p.nq) {
       for (int c = lane * 4; c < BN; c += 128)
         *reinterpret_cast<float4*>(tau_cur + c) = *reinterpret_cast<const float4*>(p.tau + q0 + c);
     } else {
       for (int c = lane; c < BN; c += 32) tau_cur[c] = (q0 + c < p.nq) ? p.tau[q0 + c] : INFINITY;
     }
+    if (local > 0) flush_issue(p, ws, sb ^ 1, lane, pend);
   }
   __syncwarp();
   if (lane == 0) ws.count[sb ^ 1] = 0;  // every lane has read it; next pushed to two items from now
@@ -712,25 +714,36 @@ struct Tc2Config {
   static constexpr uint32_t kTmemCols = (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128 : (2 * kAccCols <= 256) ? 256 : 512;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kExtra;
   static_assert(kStages >= 3, "pipeline too shallow");
+  static constexpr int kMaxStagesRes = 12;  // resident variant: barrier slots (2 * 12 + 6 words fit the 256-byte area)
 };
 
-template <int BN, int T>
+// RES (one term, one query tile, BN <= 128): the CTA's half of the query tile — all K chunks of it, kchunks x BN/2
+// rows x 128 B (48 KB at 64 queries x 768 dims, 96 KB at 128) — is loaded ONCE into shared memory and stays there;
+// the ring then carries corpus boxes only (10 / 7 stages of 16 KB). The L2 -> SM path, which caps these kernels at
+// ~6300 B/clk for the whole chip (B300_MICROARCH.md "LTS throughput cap"), carries the corpus bytes and nothing else:
+// 1.0x the HBM stream instead of 1.5x (64 queries, 1-CTA kernel) or 2x (128 queries).
+template <int BN, int T, bool RES = false>
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_constant__ CUtensorMap tmap_query,
                  const __grid_constant__ CUtensorMap tmap_query_last, const TcParams p) {
   using Cfg = Tc2Config<BN, T>;
-  constexpr int STAGES = Cfg::kStages;
+  static_assert(!RES || (T == 1 && BN <= 128), "resident queries: one term, at most 128 queries");
+  const int STAGES = RES ? p.n_stages : Cfg::kStages;
+  constexpr int kBarSlots = RES ? Cfg::kMaxStagesRes : Cfg::kStages;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* smem_a = smem;
-  unsigned char* smem_b = smem + STAGES * Cfg::kABytes;   // STAGES x T x [BN/2 x 128B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  // RES: [kchunks resident query boxes][STAGES corpus boxes]; else [STAGES corpus boxes][STAGES x T query boxes]
+  unsigned char* smem_res = smem;
+  unsigned char* smem_a = RES ? smem + (size_t)p.kchunks * Cfg::kBBytes : smem;
+  unsigned char* smem_b = smem + STAGES * Cfg::kABytes;   // STAGES x T x [BN/2 x 128B] (unused when RES)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(RES ? smem_a + (size_t)STAGES * Cfg::kABytes : smem + STAGES * Cfg::kStageBytes);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tfull_bar = bars + 2 * STAGES;
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* tau_s = reinterpret_cast<float*>(bars + 2 * STAGES + 6);
+  uint64_t* empty_bar = bars + kBarSlots;
+  uint64_t* tfull_bar = bars + 2 * kBarSlots;
+  uint64_t* tempty_bar = bars + 2 * kBarSlots + 2;
+  uint64_t* bfull_bar = bars + 2 * kBarSlots + 4;          // RES: the resident query boxes have landed (both CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBarSlots + 5);
+  float* tau_s = reinterpret_cast<float*>(bars + 2 * kBarSlots + 6);
   WarpStage* wst = reinterpret_cast<WarpStage*>(tau_s + 4 * BN);
 
   const int warp = threadIdx.x >> 5;
@@ -747,6 +760,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
     }
+    mbar_init(bfull_bar, 1);
     for (int w = 0; w < 4; ++w) wst[w].count[0] = wst[w].count[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -787,6 +801,13 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_query_last) : "memory");
       int stage = 0;
       uint32_t phase = 0;
+      if (RES && n_items > 0) {
+        // the CTA's half of the (only) query tile, every K chunk of it, once
+        const int q_half = (int)rank * (item_columns(p, 0, BN) / 2);
+        if (leader) mbar_expect_tx(bfull_bar, 2u * (uint32_t)p.kchunks * p.last_box_bytes);
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_2d_2sm(&tmap_query_last, bfull_bar, smem_res + (size_t)kc * Cfg::kBBytes, kc * KC, q_half, kEvictLast);
+      }
       for (int item = pair; item < n_items; item += n_pairs) {
         int ct, qt;
         item_to_tiles(p, item, ct, qt);
@@ -802,11 +823,11 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
         const uint32_t b_bytes = last_q ? p.last_box_bytes : Cfg::kBBytes;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + (uint32_t)nt_run * b_bytes));
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + (RES ? 0u : (uint32_t)nt_run * b_bytes)));
           tma_load_2d_2sm(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC, row0, corpus_policy);
 #pragma unroll
           for (int t = 0; t < T; ++t)
-            if (t < nt_run)
+            if (!RES && t < nt_run)
               tma_load_2d_2sm(qmap, &full_bar[stage], smem_b + (stage * T + t) * Cfg::kBBytes, kc * KC,
                               t * p.q_rows_pad + q0, kEvictLast);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -819,6 +840,10 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
+      if (RES && n_items > 0) {
+        mbar_wait(bfull_bar, 0);  // resident query boxes of both CTAs
+        tcgen05_fence_after();
+      }
       for (int item = pair; item < n_items; item += n_pairs, ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
@@ -835,7 +860,8 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
           tcgen05_fence_after();
           const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
           if constexpr (!Cfg::kDual) {
-            const uint64_t db = make_desc_sw128(smem_u32(smem_b + (stage * T) * Cfg::kBBytes));
+            const uint64_t db = make_desc_sw128(smem_u32(RES ? smem_res + (size_t)kc * Cfg::kBBytes
+                                                             : smem_b + (stage * T) * Cfg::kBBytes));
 #pragma unroll
             for (int k = 0; k < KC / UMMA_K; ++k)
               umma_f16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_item, (kc | k) != 0 ? 1u : 0u);
@@ -958,6 +984,11 @@ bool raster_enabled() {
   static const char* env = std::getenv("VODB_RASTER");
   return env ? (env[0] != '0') : true;
 }
+// VODB_RESIDENT=0 keeps the queries streaming through the ring (A/B comparisons)
+bool resident_enabled() {
+  static const char* env = std::getenv("VODB_RESIDENT");
+  return env ? (env[0] != '0') : true;
+}
 bool use_pair_kernel(const SegmentArgs& a) { return pair_kernel_enabled() && a.terms == 1 && a.planes == 1 && a.nq > 128; }
 
 // corpus tensor map (cached in the store): the rows themselves (bf16 / fp16 store), or the bf16 planes of an fp32
@@ -997,6 +1028,7 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
 
   TcParams p;
   p.last_box_bytes = (uint32_t)last_cols * KC * 2;
+  p.n_stages = 0;
   p.row_begin = a.row_begin;
   p.row_end = a.row_end;
   p.nq = a.nq;
@@ -1026,10 +1058,13 @@ int launch_bn(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   return VODB_OK;
 }
 
-template <int BN, int T>
-int launch_pair(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream_t stream) {
+template <int BN, int T, bool RES = false>
+int launch_pair(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream_t stream, int res_stages = 0) {
   using Cfg = Tc2Config<BN, T>;
-  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&score_tc2_kernel<BN, T>), Cfg::kSmemBytes));
+  const int kchunks_all = (s->dim + KC - 1) / KC;
+  const size_t smem_bytes = RES ? (size_t)kchunks_all * Cfg::kBBytes + (size_t)res_stages * Cfg::kABytes + Cfg::kExtra
+                                : (size_t)Cfg::kSmemBytes;
+  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&score_tc2_kernel<BN, T, RES>), smem_bytes));
   const CUtensorMap* tmap_store = nullptr;
   int rc = corpus_tensor_map(s, &tmap_store);
   if (rc != VODB_OK) return rc;
@@ -1043,6 +1078,7 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream
   if (rc != VODB_OK) return rc;
   TcParams p;
   p.last_box_bytes = (uint32_t)(last_cols / 2) * KC * 2;
+  p.n_stages = res_stages;
   p.row_begin = a.row_begin;
   p.row_end = a.row_end;
   p.nq = a.nq;
@@ -1070,7 +1106,7 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1081,7 +1117,7 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  VODB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, score_tc2_kernel<BN, T>, *tmap_store, tmap_q, tmap_q_last, p));
+  VODB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, score_tc2_kernel<BN, T, RES>, *tmap_store, tmap_q, tmap_q_last, p));
   return VODB_OK;
 }
 
@@ -1120,6 +1156,19 @@ int launch_score_tensor(vodb_store* s, const SegmentArgs& a, cudaStream_t stream
     }
     if (a.planes == 2) return a.nq <= 64 ? launch_bn<64, 2, 2>(s, a, stream) : launch_bn<128, 2, 2>(s, a, stream);
     return a.nq <= 64 ? launch_bn<64, 3, 3>(s, a, stream) : launch_bn<128, 3, 3>(s, a, stream);
+  }
+  if (a.terms == 1 && a.nq <= 128 && pair_kernel_enabled() && resident_enabled()) {
+    // resident-query pair kernel when the CTA's half of the query tile (all K chunks) leaves >= 6 corpus stages
+    const int kchunks = (s->dim + KC - 1) / KC;
+    if (a.nq <= 64) {
+      using C = Tc2Config<64, 1>;
+      const int st = std::min<int>(C::kMaxStagesRes, ((int)kSmemMax - (int)C::kExtra - kchunks * (int)C::kBBytes) / (int)C::kABytes);
+      if (st >= 6) return launch_pair<64, 1, true>(s, a, kTermAlways, stream, st);
+    } else {
+      using C = Tc2Config<128, 1>;
+      const int st = std::min<int>(C::kMaxStagesRes, ((int)kSmemMax - (int)C::kExtra - kchunks * (int)C::kBBytes) / (int)C::kABytes);
+      if (st >= 6) return launch_pair<128, 1, true>(s, a, kTermAlways, stream, st);
+    }
   }
   if (use_pair_kernel(a)) return launch_pair<256, 1>(s, a, kTermAlways, stream);
   if (pair_kernel_enabled() && a.terms == 2) return launch_pair_terms<2>(s, a, stream);

@@ -249,7 +249,7 @@ select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __r
   const int q = blockIdx.x;
   pdl_launch_dependents();
   pdl_wait();  // the scoring kernel's appends must be complete and visible
-  const int n = min(cnt[q], cap);
+  const int n = min(cnt[(size_t)q * kCntStride], cap);
   float* ls = cand_s + (size_t)q * cap;
   int32_t* li = cand_i + (size_t)q * cap;
   auto load_s = [&](int i) -> float { return ls[i]; };
@@ -296,7 +296,7 @@ select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __r
         ls[j] = ord_to_float(sel_o[j]);
         li[j] = sel_i[j];
       }
-      if (threadIdx.x == 0) cnt[q] = n_sel;
+      if (threadIdx.x == 0) cnt[(size_t)q * kCntStride] = n_sel;
     }
     if (threadIdx.x == 0) tau[q] = (n >= k) ? ord_to_float(vstar) : -INFINITY;
   }
