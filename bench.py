@@ -548,9 +548,11 @@ def main():
     # kernels per search on this rank: prepare (query staging + list reset) + (score, select) per segment
     # (with N>1 the merge kernel is one more launch; the p2p exchange itself adds none, NCCL adds two collectives)
     launches_per_step = int(stats["launches"]) + (1 if world > 1 else 0)
-    traffic, traffic_src = traffic_entry("score_tc64_dram_over_algorithmic", shard_bytes) if world == 1 else (None, None)
+    traffic, traffic_src = traffic_entry("score_q64_dram_over_algorithmic", shard_bytes) if world == 1 else (None, None)
     roofline = {
-        "bound": "hbm", "kernel": "score_tc_kernel<64> (tcgen05 + TMA, fused top-k filter)",
+        "bound": "hbm",
+        "kernel": "score_tc2_kernel<64,1,resident> (cta_group::2 pair, tcgen05 + TMA, query tile resident in shared memory, "
+                  "fused top-k filter)",
         "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"],
         "algorithmic_bytes_per_search_per_gpu": shard_bytes, "score_kernel_ms_per_search": score_ms_per_search,

@@ -727,7 +727,12 @@ void vodb_store_destroy(vodb_store* s) {
     for (cudaEvent_t e : p->pool) cudaEventDestroy(e);
     delete p;
   }
-  if (s->stage) cudaFree(s->stage);
+  for (int b = 0; b < 2; ++b) {
+    if (s->stage[b]) cudaFree(s->stage[b]);
+    if (s->copied[b]) cudaEventDestroy(s->copied[b]);
+    if (s->converted[b]) cudaEventDestroy(s->converted[b]);
+  }
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   if (s->planes) cudaFree(s->planes);
   if (s->data) cudaFree(s->data);
   delete s;
@@ -753,24 +758,42 @@ int vodb_store_add(vodb_store* s, const void* rows, int src_dtype, int src_on_de
     int rc = launch_convert_rows(rows, src_dtype, s->dim, dst, s->dtype, s->pitch, n, st);
     if (rc != VODB_OK) return rc;
   } else {
-    // chunked upload through a device staging buffer (64 MiB), converted on the device
+    // chunked upload through two device staging buffers (64 MiB each), converted on the device: the copy of chunk
+    // i+1 (copy stream) overlaps the conversion of chunk i (caller's stream); one host wait at the end
     const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / ((size_t)s->dim * esz));
     size_t need = std::min<size_t>((size_t)n, chunk_rows) * s->dim * esz;
     if (need > s->stage_bytes) {
-      if (s->stage) cudaFree(s->stage);
-      s->stage = nullptr;
-      VODB_CUDA_CHECK(cudaMalloc(&s->stage, need));
+      for (int b = 0; b < 2; ++b) {
+        if (s->stage[b]) cudaFree(s->stage[b]);
+        s->stage[b] = nullptr;
+      }
+      s->stage_bytes = 0;
+      VODB_CUDA_CHECK(cudaMalloc(&s->stage[0], need));
+      VODB_CUDA_CHECK(cudaMalloc(&s->stage[1], need));
       s->stage_bytes = need;
     }
-    for (int64_t r = 0; r < n; r += (int64_t)chunk_rows) {
+    if (!s->copy_stream) {
+      VODB_CUDA_CHECK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) {
+        VODB_CUDA_CHECK(cudaEventCreateWithFlags(&s->copied[b], cudaEventDisableTiming));
+        VODB_CUDA_CHECK(cudaEventCreateWithFlags(&s->converted[b], cudaEventDisableTiming));
+      }
+    }
+    int64_t chunk = 0;
+    for (int64_t r = 0; r < n; r += (int64_t)chunk_rows, ++chunk) {
+      const int b = (int)(chunk & 1);
       int64_t m = std::min<int64_t>((int64_t)chunk_rows, n - r);
       const char* src = reinterpret_cast<const char*>(rows) + (size_t)r * s->dim * esz;
-      VODB_CUDA_CHECK(cudaMemcpyAsync(s->stage, src, (size_t)m * s->dim * esz, cudaMemcpyHostToDevice, st));
-      int rc = launch_convert_rows(s->stage, src_dtype, s->dim, dst + (size_t)r * s->pitch * dtype_size(s->dtype),
+      if (chunk >= 2) VODB_CUDA_CHECK(cudaStreamWaitEvent(s->copy_stream, s->converted[b], 0));  // buffer free again
+      VODB_CUDA_CHECK(cudaMemcpyAsync(s->stage[b], src, (size_t)m * s->dim * esz, cudaMemcpyHostToDevice, s->copy_stream));
+      VODB_CUDA_CHECK(cudaEventRecord(s->copied[b], s->copy_stream));
+      VODB_CUDA_CHECK(cudaStreamWaitEvent(st, s->copied[b], 0));
+      int rc = launch_convert_rows(s->stage[b], src_dtype, s->dim, dst + (size_t)r * s->pitch * dtype_size(s->dtype),
                                    s->dtype, s->pitch, m, st);
       if (rc != VODB_OK) return rc;
-      VODB_CUDA_CHECK(cudaStreamSynchronize(st));  // the staging buffer is reused by the next chunk
+      VODB_CUDA_CHECK(cudaEventRecord(s->converted[b], st));
     }
+    VODB_CUDA_CHECK(cudaStreamSynchronize(st));  // host buffers are consumed when the call returns (include/vodb.h)
   }
   s->n_added = std::max(s->n_added, row0 + n);
   s->planes_rows_done = std::min(s->planes_rows_done, row0);  // bf16 planes of an fp32 store: redo from here

@@ -149,8 +149,13 @@ struct vodb_store {
   void* data = nullptr;    // [n_rows, pitch] of dtype, zero padded
   int sm_count = 0;
   vodb::Workspace ws;
-  void* stage = nullptr;   // staging buffer for host->device adds
+  // host->device adds: two staging buffers; chunk i+1 is copied on `copy_stream` while chunk i is converted on the
+  // caller's stream (events order buffer reuse), so PCIe and the conversion kernel overlap
+  void* stage[2] = {nullptr, nullptr};
   size_t stage_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr};     // chunk landed in stage[b]
+  cudaEvent_t converted[2] = {nullptr, nullptr};  // stage[b] consumed by the conversion kernel
   // TMA descriptor cache for the tensor-core path (opaque CUtensorMap storage)
   alignas(64) unsigned char tmap_corpus[128];
   bool tmap_corpus_valid = false;

@@ -38,6 +38,8 @@ struct SelectSmem {
   int sel_count;
   int dup_taken;
   uint32_t min_ord;
+  uint32_t max_ord;  // first pass: largest key of the list
+  int n_top;         // first pass: entries whose top byte equals the top byte of max_ord
 };
 
 // (o desc, uidx asc) "a before b"
@@ -119,20 +121,46 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
       for (int t = tid; t < 256; t += nt) sm.hist[t] = 0;
       __syncthreads();
       if (shift == 24) {
-        // first pass: read the scores from global memory (4 independent loads in flight per thread), fill the cache
+        // First pass. A histogram of the top byte (sign + 7 exponent bits) would send most of the list to three or
+        // four bins, and shared-memory atomics on one address cost a cycle per lane: ~8 us for a 16k-entry dump
+        // list. Scores of one query nearly always have >= k entries in the top byte of their maximum, so the pass
+        // first tries exactly that bin with ballots instead of atomics: (a) read the scores (4 independent loads in
+        // flight per thread), cache the ordered images, reduce the maximum; (b) count the entries that share the
+        // maximum's top byte. If there are at least `need` of them the k-th best lies in that bin and the pass is
+        // done; otherwise (top bin too small, e.g. one outlier score) the general histogram below runs.
+        uint32_t lmax = 0u;
         int i = tid;
         for (; i + 3 * nt < n; i += 4 * nt) {
           float s0 = load_s(i), s1 = load_s(i + nt), s2 = load_s(i + 2 * nt), s3 = load_s(i + 3 * nt);
           uint32_t o0 = ord_u32(s0), o1 = ord_u32(s1), o2 = ord_u32(s2), o3 = ord_u32(s3);
           if (cached) { cache[i] = o0; cache[i + nt] = o1; cache[i + 2 * nt] = o2; cache[i + 3 * nt] = o3; }
-          atomicAdd(&sm.hist[o0 >> 24], 1); atomicAdd(&sm.hist[o1 >> 24], 1);
-          atomicAdd(&sm.hist[o2 >> 24], 1); atomicAdd(&sm.hist[o3 >> 24], 1);
+          lmax = max(max(lmax, o0), max(o1, max(o2, o3)));
         }
         for (; i < n; i += nt) {
           uint32_t o = ord_u32(load_s(i));
           if (cached) cache[i] = o;
-          atomicAdd(&sm.hist[o >> 24], 1);
+          lmax = max(lmax, o);
         }
+        if (tid == 0) { sm.max_ord = 0u; sm.n_top = 0; }
+        __syncthreads();
+        lmax = __reduce_max_sync(0xffffffffu, lmax);
+        if ((tid & 31) == 0) atomicMax(&sm.max_ord, lmax);
+        __syncthreads();
+        const uint32_t top = sm.max_ord >> 24;
+        int c = 0;
+        for (int j = tid; j < n; j += nt) c += (key(j) >> 24) == top ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if ((tid & 31) == 0 && c) atomicAdd(&sm.n_top, c);
+        __syncthreads();
+        if (sm.n_top >= need) {
+          if (tid == 0) { sm.bin = (int)top; sm.need = need; sm.n_eq = sm.n_top; }
+          __syncthreads();
+          prefix |= top << 24;
+          mask |= 0xffu << 24;
+          __syncthreads();
+          continue;
+        }
+        for (int j = tid; j < n; j += nt) atomicAdd(&sm.hist[key(j) >> 24], 1);
       } else {
         for (int i = tid; i < n; i += nt) {
           uint32_t o = key(i);
