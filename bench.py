@@ -744,11 +744,14 @@ def parity_section(np, torch, dist, corpus, args, rank, world, dev, all_ranks_tr
     nq = Q_SMALL
     xq_np = make_queries(np, 1, nq, args.store_dtype)[0]
     xq = torch.from_numpy(xq_np).to(dev)
+    has_p2p = corpus._xchg is not None
+    out["exchange_checked"] = "p2p vs nccl" if has_p2p else "nccl only (corpus created with exchange=nccl)"
     for k in (100, 1000):
         if nq * k > corpus._xchg_limits[0] * corpus._xchg_limits[1]:
             continue
-        s_p2p, i_p2p = corpus.search_device(xq, k, mode="tensor", exchange="p2p")
+        # (with --exchange nccl the corpus has no peer-mapped buffers: the NCCL result then stands in for both)
         s_nccl, i_nccl = corpus.search_device(xq, k, mode="tensor", exchange="nccl")
+        s_p2p, i_p2p = corpus.search_device(xq, k, mode="tensor", exchange="p2p") if has_p2p else (s_nccl, i_nccl)
         s_loc, i_loc = corpus.store.search_device(xq, k, mode="tensor") if corpus.hi > corpus.lo else (None, None)
         torch.cuda.synchronize()
         over = corpus.any_overflow()
