@@ -1004,6 +1004,7 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
     xd.rank = x->rank;
     xd.epoch = x->epoch;
     xd.overflow = w.overflow;
+    xd.slot_elems = x->slot;
     for (int r = 0; r < x->world; ++r) {
       xd.peer_ll[r] = reinterpret_cast<uint64_t*>(x->peer[r]) + ((size_t)parity * x->world + x->rank) * x->slot_words;
       xd.peer_flag[r] = xd.peer_ll[r] + x->slot * 3;

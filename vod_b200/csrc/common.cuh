@@ -202,7 +202,7 @@ struct SegmentArgs {
 // Cross-shard exchange fused into the final select (select.cu), NCCL-LL style: every rank's final select kernel
 // stores its [nq,k] result straight into slot `rank` of every peer's gather buffer (peer-mapped memory, NVLink
 // stores) as three 8-byte words per entry, each carrying 4 payload bytes and the 4-byte epoch tag of the call:
-//   w0 = epoch<<32 | score bits, w1 = epoch<<32 | id[31:0], w2 = epoch<<32 | id[63:32].
+//   w0 = epoch<<32 | score bits, w1 = epoch<<32 | id[31:0], w2 = epoch<<32 | id[63:32]   (one plane per word).
 // An aligned 8-byte store is single-copy atomic, so a reader that sees the tag also sees the payload: no fences, no
 // flags, no counters. The merge kernel spins on the tags of the entries it needs and reduces world*k -> k.
 // Per-query candidate counters live kCntStride ints (256 bytes) apart. Atomics on addresses in one 128-byte line are
@@ -217,7 +217,10 @@ struct ExchangeDst {
   int world;
   int rank;
   uint32_t epoch;
-  uint64_t* peer_ll[kMaxPeers];  // peer r's gather buffer, slot `rank`, current parity: [nq*k][3] words
+  // peer r's gather buffer, slot `rank`, current parity: three planes [3][slot_elems] of tagged words (score, id low,
+  // id high) — plane-major so that a warp's 32 stores of one word are 256 contiguous bytes on the NVLink write path
+  uint64_t* peer_ll[kMaxPeers];
+  size_t slot_elems;             // entries per plane (max_nq * max_k of the exchange)
   // one more tagged word per (parity, source rank) behind the entries: epoch<<32 | this shard's overflow flag, so that
   // every rank learns from the exchange itself whether ANY shard overflowed (all ranks then re-run in lockstep)
   uint64_t* peer_flag[kMaxPeers];

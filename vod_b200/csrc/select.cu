@@ -329,10 +329,10 @@ select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __r
       const uint64_t w1 = tag | (uint64_t)(uint32_t)iv;
       const uint64_t w2 = tag | (uint64_t)(uint32_t)((uint64_t)iv >> 32);
       for (int r = 0; r < xd.world; ++r) {
-        uint64_t* dst = xd.peer_ll[r] + ((size_t)q * k + j) * 3;
+        uint64_t* dst = xd.peer_ll[r] + (size_t)q * k + j;  // consecutive threads -> consecutive words of a plane
         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(w0) : "memory");
-        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(w1) : "memory");
-        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 2), "l"(w2) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + xd.slot_elems), "l"(w1) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 2 * xd.slot_elems), "l"(w2) : "memory");
       }
     }
   } else if (final_pass) {
@@ -431,9 +431,10 @@ merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, in
   if (q == 0 && threadIdx.x < world) {  // did any shard overflow? (sticky, read back by the host with the results)
     if ((uint32_t)ll_wait_word(gather_ll + (size_t)threadIdx.x * slot_words + flag_word, epoch) != 0u) *overflow_any = 1;
   }
+  const size_t plane = flag_word / 3;  // entries per plane of a slot: [3][plane] tagged words, then the flag word
   auto entry = [&](int i) -> const uint64_t* {
     int l = i / k, j = i - l * k;
-    return gather_ll + (size_t)l * slot_words + ((size_t)q * k + j) * 3;
+    return gather_ll + (size_t)l * slot_words + (size_t)q * k + j;
   };
   uint32_t vstar;
   int n_sel;
@@ -446,10 +447,10 @@ merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, in
       const uint64_t* e = entry(i);
       uint64_t w[3];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w[j]) : "l"(e + j) : "memory");
+      for (int j = 0; j < 3; ++j) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w[j]) : "l"(e + j * plane) : "memory");
 #pragma unroll
       for (int j = 0; j < 3; ++j)
-        if ((uint32_t)(w[j] >> 32) != epoch) w[j] = ll_wait_word(e + j, epoch);
+        if ((uint32_t)(w[j] >> 32) != epoch) w[j] = ll_wait_word(e + j * plane, epoch);
       all_s[i] = __uint_as_float((uint32_t)w[0]);
       all_i[i] = (int64_t)((w[1] & 0xffffffffull) | (w[2] << 32));
     }
@@ -461,7 +462,7 @@ merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, in
     auto load_s = [&](int i) -> float { return __uint_as_float((uint32_t)ll_wait_word(entry(i), epoch)); };
     auto load_i = [&](int i) -> int64_t {
       const uint64_t* e = entry(i);
-      uint64_t lo = ll_wait_word(e + 1, epoch), hi = ll_wait_word(e + 2, epoch);
+      uint64_t lo = ll_wait_word(e + plane, epoch), hi = ll_wait_word(e + 2 * plane, epoch);
       return (int64_t)((lo & 0xffffffffull) | (hi << 32));
     };
     n_sel = block_select<int64_t>(load_s, load_i, n, k, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar);
@@ -473,6 +474,8 @@ merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, in
     out_i[(size_t)q * k + j] = ok ? sel_i[j] : -1;
   }
 }
+
+inline int threads_for(int n) { return n >= 8192 ? 1024 : n >= 2048 ? 512 : kSelThreads; }
 
 }  // namespace
 
@@ -487,7 +490,9 @@ int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap,
   size_t smem = (size_t)P * (sizeof(int32_t) + sizeof(uint32_t)) + (size_t)cache_n * sizeof(uint32_t);
   if (smem > 48 * 1024) VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&select_kernel<int32_t>), 160 * 1024));
   ExchangeDst none{};
-  const int threads = (nq <= 512) ? 1024 : kSelThreads;  // few queries: more threads per list; many: more CTAs per SM
+  // few queries: threads by list length (long lists want memory-level parallelism, short ones cheap barriers — a
+  // select is ~60 block barriers); many queries: small CTAs, several per SM
+  const int threads = (nq > 512) ? kSelThreads : threads_for(expected_n > 0 ? expected_n : cap);
   VODB_CUDA_CHECK(launch_pdl(select_kernel<int32_t>, dim3(nq), dim3(threads), smem, stream, cand_s, cand_i, cnt, tau, cap,
                              k, P, final_pass ? 1 : 0, out_s, out_i, row_offset, xd ? *xd : none,
                              (xd && final_pass) ? 1 : 0, cache_n));
@@ -507,7 +512,7 @@ int launch_merge_exchange(const uint64_t* gather_ll, uint32_t epoch, int world, 
   int P = pow2ceil(k), staged = 0;
   const size_t smem = merge_smem(P, world * k, &staged);
   VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&merge_exchange_kernel), smem));
-  const int threads = (nq <= 512) ? 1024 : kSelThreads;
+  const int threads = (nq > 512) ? kSelThreads : threads_for(world * k);
   VODB_CUDA_CHECK(launch_pdl(merge_exchange_kernel, dim3(nq), dim3(threads), smem, stream, gather_ll, epoch, world,
                              slot_words, flag_word, nq, k, P, staged, out_s, out_i, overflow_any));
   return VODB_OK;
@@ -518,7 +523,7 @@ int launch_merge(const float* scores, const int64_t* idx, int n_lists, int nq, i
   int P = pow2ceil(k_out), staged = 0;
   const size_t smem = merge_smem(P, n_lists * k_in, &staged);
   VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&merge_kernel), smem));
-  const int threads = (nq <= 512) ? 1024 : kSelThreads;
+  const int threads = (nq > 512) ? kSelThreads : threads_for(n_lists * k_in);
   merge_kernel<<<nq, threads, smem, stream>>>(scores, idx, n_lists, nq, k_in, k_out, P, staged, out_s, out_i);
   VODB_CUDA_CHECK(cudaGetLastError());
   return VODB_OK;
