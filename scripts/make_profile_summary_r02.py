@@ -43,7 +43,8 @@ w("All numbers from `gpurun` boxes. Peaks: `MEASURED_PEAKS.json` — HBM 6534.8 
 w("Files: `r02a_*` ncu of the 64-query scan of a 1.25M-row shard BEFORE the counter fix (raw page + source-level stall table); "
   "`r02b_*` ncu raw pages of the CTA-pair kernels (8192 one-term queries; 64 three-term queries); `r02c_*` final single-GPU "
   "state: bench line, launch list of the bench command, ncu raw page of the headline kernel, batch-size and schedule sweeps, "
-  "2-GPU bench lines (both arms) and multi-GPU test log; `r02d_*` 4- and 8-GPU bench lines and test log; "
+  "2-GPU bench lines (both arms) and multi-GPU test log; `r02d_*` 4- and 8-GPU bench lines and test log; `r02e_*` 8-GPU bench "
+  "lines after the exchange buffer became plane-major (fused and NCCL exchange, reference arm under torchrun), k = 1000 probe; "
   "`r02_sass_opcodes.txt` opcode histogram of `libvodb.so`; `traffic.json` the DRAM-traffic ratios bench.py multiplies with.\n")
 
 b1 = line("r02c_bench.json")
@@ -86,14 +87,22 @@ w("## Strong scaling on configs[1] and the north-star target shape (bench lines 
 w("| GPUs | file | 64 q: queries/s (ms) | vs 1 GPU | scoring kernels / whole step vs HBM peak | e2e ms (f32 / bf16-exact queries) | 8192 q: q/s, TFLOP/s per GPU | parity |")
 w("|---|---|---|---|---|---|---|---|")
 base = b1["value"] if b1 else None
-for n, f in ((1, "r02c_bench.json"), (2, "r02c_bench_n2.json"), (4, "r02d_bench_n4.json"), (8, "r02d_bench_n8.json")):
+for n, f in ((1, "r02c_bench.json"), (2, "r02c_bench_n2.json"), (4, "r02d_bench_n4.json"), (8, "r02d_bench_n8.json"),
+             (8, "r02e_bench_n8.json"), ("8 (NCCL all-gather + merge)", "r02e_bench_n8_nccl.json")):
     d = line(f)
     if not d:
         continue
-    r, lb = d["roofline"], d["large_batch"]
+    r, lb = d["roofline"], d.get("large_batch")
     par = d["parity"]["ok"] if d.get("parity") else "-"
-    w(f"| {n} | {f} | {d['value']:.0f} ({d['ms_per_step']:.4f}) | {d['value'] / base:.2f}x = {d['value'] / base / n:.3f} | {100 * r['frac']:.1f}% / {100 * r['whole_step_frac']:.1f}% | "
-      f"{d['e2e']['ms_per_step']:.3f} / {d['e2e']['ms_per_step_store_dtype_exact_queries']:.3f} | {lb['value']:.0f}, {lb['roofline']['achieved']:.0f} | {par} |")
+    ng = int(str(n).split()[0])
+    big = f"{lb['value']:.0f}, {lb['roofline']['achieved']:.0f}" if lb else "-"
+    w(f"| {n} | {f} | {d['value']:.0f} ({d['ms_per_step']:.4f}) | {d['value'] / base:.2f}x = {d['value'] / base / ng:.3f} | {100 * r['frac']:.1f}% / {100 * r['whole_step_frac']:.1f}% | "
+      f"{d['e2e']['ms_per_step']:.3f} / {d['e2e']['ms_per_step_store_dtype_exact_queries']:.3f} | {big} | {par} |")
+ref1, ref8 = line("r02c_bench_reference_n2.json"), line("r02e_bench_reference_n8.json")
+if ref1 and ref8:
+    w(f"\nReference arm under torchrun (rank 0 alone, BLAS threads set before numpy loads): {ref1['value']:.1f} queries/s at `--gpus 2` "
+      f"({ref1['cpu_baseline']['blas_threads']} threads), {ref8['value']:.1f} at `--gpus 8` ({ref8['cpu_baseline']['blas_threads']} threads); "
+      "round 1 fell from 31 to 6 queries/s there because torchrun exports OMP_NUM_THREADS=1.")
 w("")
 for n, f in ((2, "r02c_bench_n2.json"), (8, "r02d_bench_n8.json"), (8, "r02e_bench_n8.json")):
     d = line(f)
