@@ -151,7 +151,10 @@ w("## ncu `--set full` raw pages (per launch: ms, DRAM GB read, DRAM active %, L
 for name, what in (("r02a_small_shard_score_tc64_ncu_raw.csv", "64 queries, 1.25M-row shard, round-1 kernel and packed counters: the middle segment runs at 33% DRAM"),
                    ("r02c_q64_resident_ncu_raw.csv", "64 queries, 10M rows, headline kernel (resident queries): 3 segments"),
                    ("r02b_pair64x3_q64_ncu_raw.csv", "64 float32 queries with three real bf16 terms, `score_tc2_kernel<64,3>`: neither DRAM nor tensor pipe saturated"),
-                   ("r02b_pair256_q8192_ncu_raw.csv", "8192 queries, `score_tc2_kernel<256,1>` with the blocked item order, segments 3-7: DRAM read = 1.02x algorithmic (2.86x in round 1)")):
+                   ("r02b_pair256_q8192_ncu_raw.csv", "8192 queries, `score_tc2_kernel<256,1>` with the blocked item order, segments 3-7: DRAM read = 1.02x algorithmic (2.86x in round 1)"),
+                   ("r02f_aux_kernels_ncu_raw.csv", "the kernels beside the 16-bit tensor scan (scripts/ncu_aux_probe.py, 1M x 768): `score_exact_kernel` after its round-1 rewrite (64 queries: "
+                    "2.29 ms = 43 TFLOP/s fp32 — test / fallback path only since `auto` serves fp32 stores from the tensor cores), `split_planes_kernel`, the fp32-store tensor "
+                    "kernel `score_tc_kernel<64,3,3>` (0.73 ms for the same search, DRAM 76% on its 4.6 GB of planes), selects, sampler chain, 8-list merge")):
     rows = ncu_rows(name, want)
     if not rows:
         continue
@@ -190,6 +193,29 @@ if f.exists():
         ev = b1["roofline"]["score_kernel_ms_per_search"] / b1["ms_per_step"] if b1 else float("nan")
         w(f"\nScoring kernels' share of the search under ncu: {100 * sc / tot:.1f}% ({sc:.0f} of {tot:.0f} us); from bench.py's CUDA events without "
           f"profiler: {100 * ev:.1f}%. The shares agree.\n")
+
+f = P / "r02f_launches_small_shard_ncu.csv"
+if f.exists():
+    rows = list(csv.reader(f.open()))
+    hdr, launches = None, []
+    for r in rows:
+        if "Kernel Name" in r:
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            launches.append((d["Kernel Name"].split("(")[0].replace("void vodb::<unnamed>::", "").replace("void unnamed>::", ""), d["Grid Size"],
+                             d["Block Size"], float(d["Metric Value"]) / 1e3))
+    starts = [i for i, l in enumerate(launches) if l[0].startswith("prepare_kernel")]
+    if len(starts) > 2:
+        a, b = starts[-2], starts[-1]
+        w("## One 64-query search over a 1.25M-row shard = one rank of the 8-GPU split, per launch (r02f_launches_small_shard_ncu.csv; cold cache, serialised)\n")
+        w("| kernel | grid x block | us |\n|---|---|---|")
+        for k, g, blk, us in launches[a:b]:
+            w(f"| `{k}` | {g} x {blk} | {us:.1f} |")
+        w("\nRound 1 (r01m_launches_ncu.csv scaled to this shard): 4096-row dump 10.4 us, 86k-row segment 50 us, 1.16M-row segment ~265 us, three selects of "
+          "~11 us; now a 16384-row dump, one scan and two selects. At 8 GPUs the merge kernel (fused exchange) follows; a multi-rank command cannot be "
+          "wrapped in ncu, so the 8-GPU step is the CUDA-event time of `r02e_bench_n8.json` (0.350 ms whole step, 0.303 ms in the scoring kernels).\n")
 
 w("## Where the time of a small-shard search went (r02a_small_shard_seg1_stalls.txt)\n")
 w("Source-level stall sampling of the 86k-row middle segment before the fix: 31% of the warp samples are epilogue warps waiting for the "

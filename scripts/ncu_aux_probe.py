@@ -16,6 +16,8 @@ xq = rng.standard_normal((64, d), dtype=np.float32)
 st = vod_b200.CorpusStore(n, d, dtype="float32")
 st.fill_synthetic(1234)
 s_exact, i_exact = st.search(xq, 100, mode="exact")            # score_exact_kernel + select_kernel
+s_pl, i_pl = st.search(xq, 100)                                # auto on a float32 store: split_planes + score_tc_kernel<64,3,3>
+assert float(np.abs(s_exact - s_pl).max()) < 1e-3
 st.close()
 
 st = vod_b200.CorpusStore(n, d, dtype="bfloat16")

@@ -255,7 +255,30 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
     n_sel = min(sm.sel_count, k);
   }
 
-  if (do_sort) {
+  if (do_sort && n_sel <= nt) {
+    // Rank sort: with at most one selected entry per thread, entry i goes to position #{j : j before i} — the order
+    // is total (ids are unique within a list; equal padding entries are ordered by position), so the ranks are a permutation. One pass of n_sel broadcast reads per
+    // thread and two barriers, against log2(P)*(log2(P)+1)/2 barrier-separated stages of a bitonic network.
+    uint32_t o = 0u;
+    U id = 0;
+    int rank = 0;
+    if (tid < n_sel) {
+      o = sel_o[tid];
+      id = (U)sel_i[tid];
+      for (int j = 0; j < n_sel; ++j) {
+        const uint32_t oj = sel_o[j];
+        const U ij = (U)sel_i[j];
+        // identical (score, id) pairs exist only as padding entries of the merges; their position breaks the tie
+        rank += (before<U>(oj, ij, o, id) || (oj == o && ij == id && j < tid)) ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    if (tid < n_sel) {
+      sel_o[rank] = o;
+      sel_i[rank] = (IdxT)id;
+    }
+    __syncthreads();
+  } else if (do_sort) {
     for (int i = n_sel + tid; i < P; i += nt) {  // padding sorts last
       sel_o[i] = 0u;
       sel_i[i] = (IdxT)(~(U)0 >> 1);
