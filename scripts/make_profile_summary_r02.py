@@ -45,6 +45,8 @@ w("Files: `r02a_*` ncu of the 64-query scan of a 1.25M-row shard BEFORE the coun
   "state: bench line, launch list of the bench command, ncu raw page of the headline kernel, batch-size and schedule sweeps, "
   "2-GPU bench lines (both arms) and multi-GPU test log; `r02d_*` 4- and 8-GPU bench lines and test log; `r02e_*` 8-GPU bench "
   "lines after the exchange buffer became plane-major (fused and NCCL exchange, reference arm under torchrun), k = 1000 probe; "
+  "`r02f_*` ncu raw page of the kernels beside the scan, launch list of a small-shard search; `r02g_bench.json` bench line of the "
+  "final build (another box: 2.215 ms), `r02_compute_sanitizer.txt` memcheck / racecheck of the final build; "
   "`r02_sass_opcodes.txt` opcode histogram of `libvodb.so`; `traffic.json` the DRAM-traffic ratios bench.py multiplies with.\n")
 
 b1 = line("r02c_bench.json")

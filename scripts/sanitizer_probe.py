@@ -26,6 +26,18 @@ for dtype, modes in (("float32", ["exact", "tensor", "tensor2", "tensor3"]), ("b
         chain = vod_b200.DenseRetrievalSampler(st, top_k=20, total=4, max_pos_sections=2, mode="tensor")(xq, ref[1][:, :2].copy(), seed=1)
         assert chain.batch.indices.shape == (9, 4)
     st.close()
+# every scoring-kernel shape of round 2: resident pair kernels (<= 64 / <= 128 queries), the wide one-term pair kernel
+# with a narrow last query tile, multi-term pair kernels (<64,3>, <128,3> and the two-launch policy above 128
+# queries), blocked item order (2 query tiles), 19-row last corpus tile, k > rows in the dump segment
+st = vod_b200.CorpusStore(n + 19, 96, dtype="float16")
+st.add(np.concatenate([xb, xb[:19]]))
+for nq in ((33, 130) if small else (33, 100, 130, 300)):
+    q = rng.integers(-3, 4, size=(nq, 96)).astype(np.float32)
+    a = st.search(q, 10, mode="tensor")
+    b3 = st.search(q + np.float32(1.0 / 4096), 10, mode="tensor3")   # non-empty correction terms
+    c = st.search(q, 10, mode="tensor3")                             # empty correction terms: skipped on the device
+    assert np.array_equal(a[1], c[1]) and np.array_equal(a[0], c[0]) and b3[1].shape == (nq, 10)
+st.close()
 ms, mi = vod_b200.merge_topk(np.stack([ref[0], ref[0]]), np.stack([ref[1], ref[1] + 100000]), 20)
 b = vod_b200.RetrievalBatch(scores=ref[0], indices=ref[1])
 m, raw = hybrid.merge_search_results({"a": b, "b": vod_b200.RetrievalBatch(scores=ref[0] * 2, indices=ref[1][:, ::-1].copy())},
