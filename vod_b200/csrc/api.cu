@@ -446,15 +446,16 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
     b.push_back(n);
     return b;
   }
-  // Large batches refresh the thresholds more often (smaller first segment, growth 3 instead of up to 32): the
+  // Large batches refresh the thresholds more often (smaller first segment, growth 3 instead of up to 96): the
   // number of survivors per query over the whole scan is ~ k*g*log_{1+g}(n/first), every survivor costs epilogue
   // time, and with thousands of queries that outweighs the fixed cost of a few more (select + launch) pairs.
   // (scripts/sweep_schedule_large.py, 8192 queries: first 4096 / 16384 rows x growth 2 / 3 / 5 are within +-3% of
   // each other for k = 100 and k = 1000 — profiles/r01m_schedule_sweep_large.jsonl.)
   const bool large_batch = nq > 256;
-  // first segment ("dump": every score stored, then one select). Measured on B200 (scripts/sweep_schedule.py,
-  // 64 queries, k=100): 1024..8192 rows and growth 8..32 are within ~1% of each other on a 10M-row shard; on a
-  // 1.25M-row shard (8-GPU split) 4096/8192 rows with growth >= 20 (3 segments) beat 1024/2048 rows by ~7%.
+  // first segment ("dump": every score stored, then one select). Measured on B200, 64 queries, k=100
+  // (profiles/r02c_schedule_sweep.jsonl, after the per-query counters were spread over cache lines): 4096 rows x
+  // growth 20-32, 8192 x 64, 16384 x 80-160 and 32768 x 40 are within 2% of each other on a 1.25M-row and on a
+  // 10M-row shard; 16384 rows with the widest growth has the fewest launches (2 resp. 3 segments).
   int64_t first = round128(std::min<int64_t>(cap / 2, std::max<int64_t>(large_batch ? 4096 : 16384, 16LL * k)));
   if (large_batch) first = std::min<int64_t>(first, std::max<int64_t>(4096, round128(4LL * k)));
   // tuning knobs (development): VODB_FIRST_ROWS / VODB_GROWTH override the schedule of small batches

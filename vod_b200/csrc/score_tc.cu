@@ -3,19 +3,25 @@
 // Replaces the scoring half of `faiss_index.search(query_vec, k)` when the index is served from GPUs
 // (reference src/vod_search/faiss_search/server.py:51-54,84: GpuIndexFlat shards with useFloat16 storage,
 // src/vod_configs/search.py:52,71 — cuBLAS GEMM + faiss k-select, score matrix through HBM). Here the
-// [corpus rows x queries] score tile lives only in TMEM:
+// [corpus rows x queries] score tile lives only in TMEM. Two kernel families share one structure:
 //
-//   warp 0 (1 thread)  TMA producer: streams 128-row x 64-col corpus boxes and BN-row x 64-col query boxes
-//                      (128-byte swizzle) through a STAGES-deep mbarrier ring;
-//   warp 1 (1 thread)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 (corpus rows), N=BN (queries),
-//                      K=16 per instruction, fp32 accumulation in one of two TMEM accumulator buffers;
+//   warp 0 (1 thread)  TMA producer: streams 128-row x 64-col corpus boxes (and, unless the query tile is resident
+//                      in shared memory, the query boxes; 128-byte swizzle) through an mbarrier ring;
+//   warp 1 (1 thread)  MMA issuer: tcgen05.mma kind::f16, M = corpus rows, N = queries (x terms), K=16 per
+//                      instruction, fp32 accumulation in one of two TMEM accumulator buffers;
 //   warps 2..5         epilogue: tcgen05.ld 32 lanes x 32 columns, compare every score with the query's
 //                      running threshold tau[q] (k-th best so far, select.cu) and append the rare survivors
-//                      to the per-query candidate list with one warp-aggregated atomic.
+//                      to the per-query candidate list (per-warp staging, deferred slot-reserving atomics).
 //
-// D (accumulator) row i = TMEM lane i = corpus row; column j = query j of the tile. Persistent CTAs
-// (one per SM) walk (corpus tile, query tile) items with the query tile fastest, so that co-resident CTAs
-// share the same corpus tile in L2 when nq > BN.
+//   score_tc2_kernel<BN, T, RES>  CTA pairs (cta_group::2): 256 corpus rows x BN queries x T query terms per item, each
+//                      CTA staging its own 128 rows and its own half of the queries; RES keeps that half resident.
+//                      Every 16-bit-store search runs here.
+//   score_tc_kernel<BN, T, P>     one CTA per item (cta_group::1): fp32 stores through P bf16 planes, shapes whose query
+//                      tile does not fit the resident variant, and the VODB_TC2=0 A/B path.
+//
+// D (accumulator) row i = TMEM lane i = corpus row; column j = query j of the tile. Persistent CTAs walk
+// (corpus tile, query tile) items; with several query tiles the corpus is walked in L2-sized blocks with the query
+// tile as the slow index (TcParams::raster_tiles).
 //
 // Algorithmic work per segment: rows*pitch*2 bytes from HBM, 2*nq*rows*pitch flop.
 #include <cuda.h>
