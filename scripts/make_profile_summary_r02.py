@@ -219,6 +219,19 @@ if f.exists():
           "~11 us; now a 16384-row dump, one scan and two selects. At 8 GPUs the merge kernel (fused exchange) follows; a multi-rank command cannot be "
           "wrapped in ncu, so the 8-GPU step is the CUDA-event time of `r02e_bench_n8.json` (0.350 ms whole step, 0.303 ms in the scoring kernels).\n")
 
+mg, ing = line("r02g_multigpu_store_n2_probe.json"), line("r02g_ingest_probe.json")
+if mg and ing:
+    w("## Single-process multi-GPU master and ingest (r02g_multigpu_store_n2_probe.json, r02g_ingest_probe.json)\n")
+    w(f"`B200SearchMaster(store=MultiGpuStore(10M x 768 bf16, devices=[0, 1]))` — ONE process owning both GPUs, the reference's server shape — through "
+      f"`client.search(np.ndarray)`: p50 {mg['bf16_exact_queries']['ms_p50']:.3f} ms per 64-query batch ({mg['bf16_exact_queries']['queries_per_s']:.0f} queries/s) with "
+      f"bf16-exact float32 queries, {mg['full_f32_queries']['ms_p50']:.3f} ms with full-mantissa queries; identical to one store holding everything: "
+      f"{mg['equals_single_store']}. (One process per GPU with the fused exchange, same box class: 1.335 / 1.496 ms, table above.) The per-search "
+      "torch.stack / .cpu() chain of round 1 is gone: scans on all devices are enqueued first, lists reach the first device by event-ordered peer copies, one host wait.\n")
+    w(f"Ingest, one GPU: float32 rows in pinned host memory -> bf16 store {ing['pinned_f32_to_bf16_store_gb_per_s']:.1f} GB/s of host data in 2^18-row `add` calls, "
+      f"{ing['one_call_4gb_gb_per_s']:.1f} GB/s for one 4 GB call (two staging buffers, copy stream overlapping the conversion kernel; PCIe-bound: 52 GB/s in round 1); "
+      f"`zarr_io.ingest` from an uncompressed zarr-v2 store with the reference's 100-row chunks (2000 files of 300 KB on tmpfs): {ing['zarr_uncompressed_chunks100_gb_per_s']:.2f} GB/s, "
+      f"read-back equal: {ing['zarr_roundtrip_ok']}.\n")
+
 w("## Where the time of a small-shard search went (r02a_small_shard_seg1_stalls.txt)\n")
 w("Source-level stall sampling of the 86k-row middle segment before the fix: 31% of the warp samples are epilogue warps waiting for the "
   "next accumulator (the MMA warp is itself waiting for stages that the epilogue has not released), 16% wait for the threshold loads that "

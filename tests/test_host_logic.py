@@ -174,3 +174,27 @@ def test_b200_factory_config_mirrors_the_faiss_config_surface():
     assert isinstance(master, vod_b200.B200SearchMaster) and master.dtype == "float32" and master.store is None
     with pytest.raises(ValueError):
         vod_b200.build_b200_search([[0.0]], config={"factory": "IVF100,Flat"})
+
+
+def test_scan_schedule_invariants_for_random_shapes():
+    """Property check of the C++ planner (vodb_plan_scan): for any shard size / batch / k the segments tile the shard,
+    start on tile boundaries, the dump segment fits a list, the expected survivors of every later segment
+    (k * rows(segment) / rows(before), rows in random order) stay within an eighth of the list, and the safe schedule
+    cannot overflow."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=200, deadline=None)
+    @hyp.given(n_rows=st.integers(1, 200_000_000), nq=st.integers(1, 8192), k=st.integers(1, 2048))
+    def check(n_rows, nq, k):
+        cap, b = _plan(n_rows, nq, k)
+        assert b[0] == 0 and b[-1] == n_rows and all(x < y for x, y in zip(b, b[1:]))
+        assert all(x % 128 == 0 for x in b[:-1]) and b[1] <= cap and cap >= 4 * k
+        for lo, hi in zip(b[1:], b[2:]):
+            # growth rule: k * seg / before <= cap / 8; a tail shorter than a quarter segment is folded into the last
+            # one (x1.25) and segment lengths are rounded to 128 rows
+            assert k * (hi - lo - 128) / lo <= 1.25 * cap / 8 + 1e-9, (b, cap)
+        cap_s, bs = _plan(n_rows, nq, k, True)
+        assert all(y - x <= cap_s - k for x, y in zip(bs, bs[1:]))
+
+    check()

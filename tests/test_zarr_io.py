@@ -140,3 +140,38 @@ def test_ingest_streams_blocks_in_order(tmp_path, vectors):
     assert zarr_io.ingest(sink, zarr_io.open_vectors(p), batch_rows=300) == 1234
     assert [r for r, _ in sink.blocks] == [0, 300, 600, 900, 1200]
     assert np.array_equal(np.concatenate([b for _, b in sink.blocks]), vectors)
+
+
+def test_blosc_frames_of_random_shapes_round_trip():
+    """Property check of the blosc-1 decoder against the test-side frame encoder: random payload sizes (including
+    sizes that leave a short last block and bytes that do not fill an element), type sizes, block sizes, split /
+    unsplit blocks, compressible and incompressible data."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=60, deadline=None)
+    @hyp.given(n=st.integers(1, 20_000), typesize=st.sampled_from([1, 2, 4, 8]), blocksize=st.sampled_from([512, 4096, 6000]),
+               split=st.booleans(), cname=st.sampled_from(["lz4", "zstd"]), compressible=st.booleans(), seed=st.integers(0, 2**31))
+    def check(n, typesize, blocksize, split, cname, compressible, seed):
+        rng = np.random.default_rng(seed)
+        data = (rng.integers(0, 4, size=n) if compressible else rng.integers(0, 256, size=n)).astype(np.uint8).tobytes()
+        frame = _blosc_frame(data, typesize, blocksize, split and typesize > 1, cname)
+        assert zarr_io.blosc_decode(frame) == data
+
+    check()
+
+
+def test_row_slicing_matches_numpy_for_random_requests(tmp_path):
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(357, 20)).astype(np.float32)
+    _write_raw_zarr(tmp_path / "s", a, 50, compressor={"id": "zlib", "level": 1}, encode=lambda b: zlib.compress(b, 1))
+    arr = zarr_io.ZarrV2Array(tmp_path / "s", threads=2)
+
+    @hyp.settings(max_examples=80, deadline=None)
+    @hyp.given(start=st.integers(-400, 400), stop=st.integers(-400, 800), step=st.sampled_from([1, 2, 7, -1, -3]))
+    def check(start, stop, step):
+        assert np.array_equal(arr[start:stop:step], a[start:stop:step])
+
+    check()

@@ -13,6 +13,7 @@
 //      front of the list and tau[q] := v* becomes the filter threshold of the next scan segment.
 // Exact (no approximation): the order is total because ids are unique within a list.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -498,7 +499,11 @@ merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, in
   }
 }
 
-inline int threads_for(int n) { return n >= 8192 ? 1024 : n >= 2048 ? 512 : kSelThreads; }
+inline int threads_for(int n) {
+  static const char* env = std::getenv("VODB_SEL_THREADS");  // development knob (scripts/r02_sweep_select.py)
+  if (env) return std::max(64, std::min(1024, std::atoi(env) / 32 * 32));
+  return n >= 8192 ? 1024 : n >= 2048 ? 512 : kSelThreads;
+}
 
 }  // namespace
 
