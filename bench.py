@@ -608,7 +608,10 @@ def main():
     # ---- multi-GPU parity (untimed): the merged result is right, on every rank ----
     parity = None
     if world > 1 and not args.no_parity:
-        parity = parity_section(np, torch, dist, corpus, args, rank, world, dev, all_ranks_true)
+        try:
+            parity = parity_section(np, torch, dist, corpus, args, rank, world, dev, all_ranks_true)
+        except Exception as exc:  # a failed check must show up in the line, not take the line down
+            parity = {"ok": False, "error": f"{type(exc).__name__}: {exc}"}
 
     # ---- BASELINE configs[3]: RealmCollate-style chain, 32 queries -> top-1000 -> priority sampling of 8 (rank 0) ----
     config4 = None
