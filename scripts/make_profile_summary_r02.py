@@ -63,10 +63,11 @@ if b1:
       "`l1tex__m_xbar2l1tex_read_bytes` 15.40 GB: the L2 -> SM path carries the corpus and nothing else |")
     w(f"| kernels per search | {b1['gpu_launches_per_step']} (prepare + {b1['segments']} x (score, select)), list capacity {b1['cap']} (9, 4 segments) |")
     w(f"| select kernels per search | {1e3 * r['select_kernel_ms_per_search']:.1f} us |")
-    w(f"| e2e `B200SearchClient.search(np.ndarray)`, float32 queries with full mantissas (3 query terms really scored) | "
-      f"{e['value']:.0f} queries/s, {e['ms_per_step']:.3f} ms |")
-    w(f"| e2e, float32 queries that are exact in bf16 (what round 1 timed; correction terms skipped on the device) | "
-      f"{e['value_store_dtype_exact_queries']:.0f} queries/s, {e['ms_per_step_store_dtype_exact_queries']:.3f} ms (25149, 2.545) |")
+    full_v = e.get("value_full_mantissa_f32_queries", e["value"])
+    full_ms = e.get("ms_per_step_full_mantissa_f32_queries", e["ms_per_step"])
+    w(f"| e2e `B200SearchClient.search(np.ndarray)`, float32 queries holding bf16 values (bf16-mixed encoder, as round 1 timed; correction terms "
+      f"skipped on the device) | {e['value_store_dtype_exact_queries']:.0f} queries/s, {e['ms_per_step_store_dtype_exact_queries']:.3f} ms (25149, 2.545) |")
+    w(f"| e2e, float32 queries with full mantissas (3 query terms really scored) | {full_v:.0f} queries/s, {full_ms:.3f} ms |")
     w(f"| per-call latency p10 / p50 / p90 | {b1['latency']['p10']:.3f} / {b1['latency']['p50']:.3f} / {b1['latency']['p90']:.3f} ms |")
     w(f"| 8192-query batches (`score_tc2_kernel<256,1>`) | {lb['value']:.0f} queries/s, {lb['ms_per_step']:.1f} ms; scoring kernels "
       f"{lb['roofline']['achieved']:.0f} TFLOP/s = {100 * lb['roofline']['frac']:.1f}% of burst, {100 * lb['roofline']['frac_of_sustained']:.1f}% of sustained; "
@@ -99,7 +100,7 @@ for n, f in ((1, "r02c_bench.json"), (2, "r02c_bench_n2.json"), (4, "r02d_bench_
     ng = int(str(n).split()[0])
     big = f"{lb['value']:.0f}, {lb['roofline']['achieved']:.0f}" if lb else "-"
     w(f"| {n} | {f} | {d['value']:.0f} ({d['ms_per_step']:.4f}) | {d['value'] / base:.2f}x = {d['value'] / base / ng:.3f} | {100 * r['frac']:.1f}% / {100 * r['whole_step_frac']:.1f}% | "
-      f"{d['e2e']['ms_per_step']:.3f} / {d['e2e']['ms_per_step_store_dtype_exact_queries']:.3f} | {big} | {par} |")
+      f"{d['e2e'].get('ms_per_step_full_mantissa_f32_queries', d['e2e']['ms_per_step']):.3f} / {d['e2e']['ms_per_step_store_dtype_exact_queries']:.3f} | {big} | {par} |")
 ref1, ref8 = line("r02c_bench_reference_n2.json"), line("r02e_bench_reference_n8.json")
 if ref1 and ref8:
     w(f"\nReference arm under torchrun (rank 0 alone, BLAS threads set before numpy loads): {ref1['value']:.1f} queries/s at `--gpus 2` "
