@@ -939,200 +939,6 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
   }
 }
 
-// ---- wide variant: 256 corpus rows x 512 queries per pair item -------------------------------------------------------
-//
-// The <256,1> pair kernel is bound by how fast stages arrive, not by the tensor pipe: ~630 cycles per stage whatever the
-// MMA width (ncu, profiles/r02h_*: 82% tensor activity at 256 columns per stage, 62% when the second query tile is 128
-// wide), i.e. by the bytes in flight per SM (6 stages x 32 KB) over the L2 / HBM latency. This variant spends the same
-// bytes in flight on more work: a stage carries the CTA's 128 corpus rows and its halves of TWO 256-query tiles (48 KB,
-// 4 stages), and each K step issues two MMAs (N = 256 each, the second as wide as the queries left) on the same corpus
-// tile — 2/3 of the operand bytes per flop. The two accumulators fill all 512 TMEM columns, so the epilogue of an item
-// no longer overlaps the MMAs of the next one; that bubble (the epilogue reads 512 columns while the pipe idles) is the
-// price, paid back whenever the batch has more than 256 queries.
-struct TcWideConfig {
-  static constexpr int BQ = 256;                              // queries per sub-tile (one MMA)
-  static constexpr int BN = 2 * BQ;                           // queries per item
-  static constexpr uint32_t kABytes = BM * KC * 2;            // this CTA's 128 corpus rows
-  static constexpr uint32_t kBBytes = (BQ / 2) * KC * 2;      // this CTA's half of one sub-tile
-  static constexpr uint32_t kStageBytes = kABytes + 2 * kBBytes;
-  static constexpr int kStages = 4;
-  static constexpr uint32_t kTmemCols = 512;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256 + 4 * BN * sizeof(float) + 4 * sizeof(WarpStage);
-  static_assert(kSmemBytes <= kSmemMax, "wide pair kernel does not fit shared memory");
-};
-
-__global__ void __launch_bounds__(kThreads, 1)
-score_tc2w_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_constant__ CUtensorMap tmap_query,
-                  const __grid_constant__ CUtensorMap tmap_query_last, const TcParams p) {
-  using Cfg = TcWideConfig;
-  constexpr int STAGES = Cfg::kStages;
-  constexpr int BN = Cfg::BN, BQ = Cfg::BQ;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* smem_a = smem;                                   // STAGES x [128 x 128B]
-  unsigned char* smem_b = smem + STAGES * Cfg::kABytes;           // STAGES x 2 x [128 x 128B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tfull_bar = bars + 2 * STAGES;       // [1]: both accumulators of the item are complete
-  uint64_t* tempty_bar = bars + 2 * STAGES + 1;  // [1]: the 8 epilogue warps of the pair have drained them
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
-  float* tau_s = reinterpret_cast<float*>(bars + 2 * STAGES + 4);
-  WarpStage* wst = reinterpret_cast<WarpStage*>(tau_s + 4 * BN);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 8);
-    for (int w = 0; w < 4; ++w) wst[w].count[0] = wst[w].count[1] = 0;
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  cluster_sync_all();
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(Cfg::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  const int n_pairs = gridDim.x >> 1;
-  const int pair = blockIdx.x >> 1;
-  int n_items = p.n_ctiles * p.n_qtiles;  // 256-row pair tiles x 512-query groups
-  if (p.term_policy != kTermAlways) {
-    int m = 0;
-    for (int i = threadIdx.x; i < p.term_blocks; i += kThreads) m |= p.term_any[i];
-    const int multi = __syncthreads_or(m & 6);
-    if (p.term_policy == kOnlyIfSingleTerm && multi) n_items = 0;  // the multi-term launch has this batch
-  }
-  const int last_sub = (p.nq - 1) / BQ;  // index of the batch's last 256-query sub-tile (the one with the narrow box)
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer (both CTAs) ----------------
-      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_corpus) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_query) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_query_last) : "memory");
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = pair; item < n_items; item += n_pairs) {
-        int ct, qt;
-        item_to_tiles(p, item, ct, qt);
-        const int row0 = (int)(p.row_begin + ((int64_t)ct * 2 + rank) * BM);
-        const int qa = qt * BN, qb = qa + BQ;
-        const int n0 = item_columns(p, qa, BQ), n1 = qb < p.nq ? item_columns(p, qb, BQ) : 0;
-        const bool last0 = (2 * qt == last_sub), last1 = (2 * qt + 1 == last_sub);
-        const uint32_t bytes0 = last0 ? p.last_box_bytes : Cfg::kBBytes;
-        const uint32_t bytes1 = n1 == 0 ? 0u : (last1 ? p.last_box_bytes : Cfg::kBBytes);
-        const uint64_t corpus_policy =
-            (p.n_qtiles == 1 || (p.raster_tiles > 0 && qt == p.n_qtiles - 1)) ? kEvictFirst : kEvictLast;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + bytes0 + bytes1));
-          tma_load_2d_2sm(&tmap_corpus, &full_bar[stage], smem_a + stage * Cfg::kABytes, kc * KC, row0, corpus_policy);
-          tma_load_2d_2sm(last0 ? &tmap_query_last : &tmap_query, &full_bar[stage], smem_b + (stage * 2) * Cfg::kBBytes,
-                          kc * KC, qa + (int)rank * (n0 / 2), kEvictLast);
-          if (n1 > 0)
-            tma_load_2d_2sm(last1 ? &tmap_query_last : &tmap_query, &full_bar[stage],
-                            smem_b + (stage * 2 + 1) * Cfg::kBBytes, kc * KC, qb + (int)rank * (n1 / 2), kEvictLast);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ---------------- MMA issuer (leader only, for the pair) ----------------
-      int stage = 0;
-      uint32_t phase = 0;
-      int local = 0;
-      for (int item = pair; item < n_items; item += n_pairs, ++local) {
-        int ct, qt;
-        item_to_tiles(p, item, ct, qt);
-        const int qa = qt * BN, qb = qa + BQ;
-        const int n0 = item_columns(p, qa, BQ), n1 = qb < p.nq ? item_columns(p, qb, BQ) : 0;
-        const uint32_t idesc0 = idesc_with_n(p.idesc, n0), idesc1 = idesc_with_n(p.idesc, n1 > 0 ? n1 : BQ);
-        mbar_wait(tempty_bar, (uint32_t)(local & 1) ^ 1);  // the epilogue has drained the previous item
-        tcgen05_fence_after();
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t db0 = make_desc_sw128(smem_u32(smem_b + (stage * 2) * Cfg::kBBytes));
-          const uint64_t db1 = make_desc_sw128(smem_u32(smem_b + (stage * 2 + 1) * Cfg::kBBytes));
-#pragma unroll
-          for (int k = 0; k < KC / UMMA_K; ++k) {
-            umma_f16_2sm(tmem_base, da + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc0, (kc | k) != 0 ? 1u : 0u);
-            if (n1 > 0)
-              umma_f16_2sm(tmem_base + (uint32_t)BQ, da + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc1,
-                           (kc | k) != 0 ? 1u : 0u);
-          }
-          umma_commit_2sm(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit_2sm(tfull_bar);
-      }
-    }
-  } else {
-    // ---------------- epilogue warps (2..5) of both CTAs ----------------
-    const int quarter = warp & 3;
-    const int ew = warp - 2;
-    WarpStage& ws = wst[ew];
-    float* tau_cur = tau_s + ew * BN;
-    int local = 0;
-    PendingFlush pend;
-#pragma unroll
-    for (int u = 0; u < kFlushPerLane; ++u) pend.pos[u] = -1;
-    for (int item = pair; item < n_items; item += n_pairs, ++local) {
-      int ct, qt;
-      item_to_tiles(p, item, ct, qt);
-      const int q0 = qt * BN;
-      const int sb = local & 1;
-      epilogue_begin_item<BN>(p, ws, tau_cur, q0, sb, local, lane, pend);
-
-      const int64_t row = p.row_begin + ((int64_t)ct * 2 + rank) * BM + quarter * 32 + lane;
-      const bool valid = row < p.row_end;
-      // columns the item's MMAs wrote: [0, n0) if there is no second sub-tile (then n0 may be < 256), else [0, 256 + n1)
-      const int n1 = q0 + BQ < p.nq ? item_columns(p, q0 + BQ, BQ) : 0;
-      const int n_cols = n1 > 0 ? BQ + n1 : item_columns(p, q0, BQ);
-
-      mbar_wait(tfull_bar, (uint32_t)(local & 1));
-      tcgen05_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      epilogue_columns<BN>(p, ws, tau_cur, taddr0, row, valid, q0, sb, 1, n_cols);
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cta(tempty_bar, 0);
-      flush_complete(p, pend);
-    }
-    __syncwarp();
-    if (!p.dump && local > 0) {
-      flush_issue(p, ws, (local - 1) & 1, lane, pend);
-      flush_complete(p, pend);
-    }
-  }
-
-  tcgen05_fence_before();
-  cluster_sync_all();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols)
-                 : "memory");
-  }
-}
-
 // ---- host side -------------------------------------------------------------------
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1321,74 +1127,6 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream
   return VODB_OK;
 }
 
-int launch_pair_wide(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream_t stream) {
-  using Cfg = TcWideConfig;
-  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&score_tc2w_kernel), Cfg::kSmemBytes));
-  const CUtensorMap* tmap_store = nullptr;
-  int rc = corpus_tensor_map(s, &tmap_store);
-  if (rc != VODB_OK) return rc;
-  alignas(64) CUtensorMap tmap_q, tmap_q_last;
-  const int64_t q_rows_pad = ((int64_t)a.nq + 255) / 256 * 256;
-  rc = encode_2d(&tmap_q, a.queries, a.dtype, q_rows_pad, s->pitch, Cfg::BQ / 2);
-  if (rc != VODB_OK) return rc;
-  const int last_cols = std::min(Cfg::BQ, ((a.nq - ((a.nq - 1) / Cfg::BQ) * Cfg::BQ) + 31) / 32 * 32);
-  rc = encode_2d(&tmap_q_last, a.queries, a.dtype, q_rows_pad, s->pitch, last_cols / 2);
-  if (rc != VODB_OK) return rc;
-  TcParams p;
-  p.last_box_bytes = (uint32_t)(last_cols / 2) * KC * 2;
-  p.n_stages = 0;
-  p.row_begin = a.row_begin;
-  p.row_end = a.row_end;
-  p.nq = a.nq;
-  p.n_ctiles = (int)((a.row_end - a.row_begin + 2 * BM - 1) / (2 * BM));
-  p.n_qtiles = (a.nq + Cfg::BN - 1) / Cfg::BN;
-  p.kchunks = (s->dim + KC - 1) / KC;
-  p.q_rows_pad = (int)q_rows_pad;
-  p.plane_rows = 0;
-  p.cand_s = a.cand_s;
-  p.cand_i = a.cand_i;
-  p.cnt = a.cnt;
-  p.tau = a.tau;
-  p.overflow = a.overflow;
-  p.cap = a.cap;
-  p.dump = a.dump ? 1 : 0;
-  p.term_any = a.term_any;
-  p.term_blocks = a.term_blocks;
-  p.term_policy = term_policy;
-  const uint32_t fmt = (a.dtype == VODB_BF16) ? 1u : 0u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Cfg::BQ >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
-  int64_t items = (int64_t)p.n_ctiles * p.n_qtiles;
-  if (items <= 0) return VODB_OK;
-  int pairs = (int)std::min<int64_t>(items, s->sm_count / 2);
-  p.raster_tiles = (p.n_qtiles > 1 && raster_enabled()) ? pairs : 0;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 2;
-  VODB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, score_tc2w_kernel, *tmap_store, tmap_q, tmap_q_last, p));
-  return VODB_OK;
-}
-
-// one-term batches above 256 queries: the wide pair kernel (two query tiles per corpus tile); VODB_WIDE=0 keeps <256,1>
-bool wide_enabled() {
-  static const char* env = std::getenv("VODB_WIDE");
-  return env ? (env[0] != '0') : true;
-}
-int launch_one_term_large(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream_t stream) {
-  if (a.nq > 256 && wide_enabled()) return launch_pair_wide(s, a, term_policy, stream);
-  return launch_pair<256, 1>(s, a, term_policy, stream);
-}
-
 // multi-term scan of a 16-bit store on CTA pairs. Batches above 128 queries are launched twice — the wide one-term
 // kernel, which works only if the correction terms turn out empty on the device (float32 queries that are exact in
 // the store dtype), and the multi-term kernel, which works only if they do not: exactly one of them finds items.
@@ -1396,7 +1134,7 @@ template <int T>
 int launch_pair_terms(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   if (a.nq <= 64) return launch_pair<64, T>(s, a, kTermAlways, stream);
   if (a.nq <= 128) return launch_pair<128, T>(s, a, kTermAlways, stream);
-  int rc = launch_one_term_large(s, a, kOnlyIfSingleTerm, stream);
+  int rc = launch_pair<256, 1>(s, a, kOnlyIfSingleTerm, stream);
   if (rc != VODB_OK) return rc;
   return launch_pair<128, T>(s, a, kOnlyIfMultiTerm, stream);
 }
@@ -1438,7 +1176,7 @@ int launch_score_tensor(vodb_store* s, const SegmentArgs& a, cudaStream_t stream
       if (st >= 6) return launch_pair<128, 1, true>(s, a, kTermAlways, stream, st);
     }
   }
-  if (use_pair_kernel(a)) return launch_one_term_large(s, a, kTermAlways, stream);
+  if (use_pair_kernel(a)) return launch_pair<256, 1>(s, a, kTermAlways, stream);
   if (pair_kernel_enabled() && a.terms == 2) return launch_pair_terms<2>(s, a, stream);
   if (pair_kernel_enabled() && a.terms == 3) return launch_pair_terms<3>(s, a, stream);
   switch (a.terms) {  // 1-CTA kernels: one term up to 128 queries; everything when VODB_TC2=0
