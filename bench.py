@@ -65,7 +65,7 @@ def parse_args():
     p.add_argument("--no-target", action="store_true", help="skip the 100M-row target-config section (N>1)")
     p.add_argument("--no-parity", action="store_true", help="skip the untimed multi-GPU parity section (N>1)")
     p.add_argument("--target-rows", type=int, default=TARGET_ROWS)
-    p.add_argument("--large-steps", type=int, default=3)
+    p.add_argument("--large-steps", type=int, default=5)
     p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="cross-shard exchange (N>1)")
     p.add_argument("--top-k", type=int, default=TOP_K, help="results per query (BASELINE configs[2] uses 1000)")
     p.add_argument("--store-dtype", default="bfloat16", choices=["bfloat16", "float16"],
