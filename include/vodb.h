@@ -178,7 +178,9 @@ void vodb_xchg_destroy(vodb_xchg* x);
  *   - host outputs: the call itself re-runs the batch on the overflow-proof schedule, on all ranks in lockstep;
  *   - device outputs (enqueue only): vodb_search_check() returns the same answer on every rank; callers that see 1
  *     re-run the batch with safe=1 on ALL ranks.
- * `safe` != 0 selects the overflow-proof schedule from the start (all ranks must pass the same value). */
+ * `safe` != 0 selects the overflow-proof schedule from the start (all ranks must pass the same value).
+ * The flag word also carries a fingerprint of (nq, k): ranks that run an epoch with different batch shapes do not
+ * hang in the merge; the host-output call returns VODB_ESTATE, vodb_search_check() does after a device-output call. */
 int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_dtype, int q_on_device, int nq,
                         int k, int mode, int safe, float* out_scores, int64_t* out_idx, int out_on_device,
                         void* stream);

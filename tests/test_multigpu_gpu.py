@@ -82,6 +82,20 @@ def _worker(rank: int, world: int, port: int, q):
                 torch.cuda.synchronize()
                 if not corpus.any_overflow():  # asynchronous path: every rank must learn about the overflow
                     ok, msg = False, f"rank {rank}: any_overflow() missed another shard's overflow"
+                # ranks that disagree on the batch shape must not hang in the merge: the shape travels with the
+                # overflow flag, every rank sees the mismatch and the next check raises
+                bad_nq = 8 if rank == 0 else 16
+                corpus.search_device(torch.from_numpy(np.tile(aq, (6, 1))[:bad_nq].copy()).cuda(), 100, mode="tensor")
+                torch.cuda.synchronize()
+                try:
+                    corpus.any_overflow()
+                    ok, msg = False, f"rank {rank}: mismatched batch shapes were not reported"
+                except vod_b200.VodbError as exc:
+                    if "batch shapes" not in str(exc):
+                        ok, msg = False, f"rank {rank}: unexpected error {exc}"
+                res = master.get_client().search(vector=aq, top_k=100)   # and the corpus keeps working afterwards
+                if not np.array_equal(res.indices, ri):
+                    ok, msg = False, f"rank {rank}: search after a reported mismatch is wrong"
             corpus.close()
         dist.barrier()
     except Exception as exc:  # report instead of hanging the other rank

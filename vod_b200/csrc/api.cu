@@ -1031,6 +1031,11 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
     std::memcpy(&flag, w.out_host + nqk * 12, sizeof(int));
     if (flag == 0) break;
     VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, 2 * sizeof(int), st));
+    if (flag & 2) {
+      set_error("vodb_search_sharded: the ranks did not pass the same batch shape (nq=%d, k=%d here): every rank must call "
+                "with the same queries, in the same order", nq, k);
+      return VODB_ESTATE;
+    }
     if (safe_run) {
       set_error("vodb_search_sharded: candidate list overflow in safe mode (internal error)");
       return VODB_ESTATE;
@@ -1066,6 +1071,10 @@ int vodb_search_check(vodb_store* s, void* stream) {
   VODB_CUDA_CHECK(cudaMemcpyAsync(w.overflow_host, w.overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   VODB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, 2 * sizeof(int), st));
   VODB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (w.overflow_host[1] & 2) {
+    set_error("vodb_search_check: a sharded search ran with different batch shapes (nq, k) on different ranks");
+    return VODB_ESTATE;
+  }
   return (w.overflow_host[0] | w.overflow_host[1]) != 0 ? 1 : 0;
 }
 

@@ -342,7 +342,11 @@ select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __r
     const uint64_t tag = (uint64_t)xd.epoch << 32;
     if (q == 0 && threadIdx.x == 0) {
       // every scoring kernel of this search has completed (stream order): the shard's overflow flag is final
-      const uint64_t f = tag | (uint64_t)(*reinterpret_cast<const volatile int*>(xd.overflow) != 0 ? 1u : 0u);
+      // payload: bit 0 = this shard's overflow flag, bits 1.. = fingerprint of the batch shape (nq, k): ranks that call
+      // with different shapes would read each other's slots at the wrong offsets without anyone noticing
+      const uint32_t shape = ((uint32_t)gridDim.x * 2654435761u) ^ ((uint32_t)k * 40503u);
+      const uint64_t f = tag | (uint64_t)(((shape & 0x7fffffffu) << 1) |
+                                          (*reinterpret_cast<const volatile int*>(xd.overflow) != 0 ? 1u : 0u));
       for (int r = 0; r < xd.world; ++r)
         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(xd.peer_flag[r]), "l"(f) : "memory");
     }
@@ -452,8 +456,29 @@ merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, in
   pdl_wait();  // this rank's final select (which also filled slot `rank` of the local gather buffer) is complete
   const int q = blockIdx.x;
   const int n = world * k;
-  if (q == 0 && threadIdx.x < world) {  // did any shard overflow? (sticky, read back by the host with the results)
-    if ((uint32_t)ll_wait_word(gather_ll + (size_t)threadIdx.x * slot_words + flag_word, epoch) != 0u) *overflow_any = 1;
+  // every block first looks at the peers' flag words (they arrive with the first block of a peer's final select):
+  // bit 0 = that shard overflowed (sticky, read back by the host with the results), the rest = the peer's batch shape.
+  // A peer that runs this epoch with another (nq, k) never writes the slots this block would wait for, so the block
+  // reports the mismatch and returns padding instead of spinning.
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const uint32_t f = (uint32_t)ll_wait_word(gather_ll + (size_t)threadIdx.x * slot_words + flag_word, epoch);
+    const uint32_t shape = (((uint32_t)nq * 2654435761u) ^ ((uint32_t)k * 40503u)) & 0x7fffffffu;
+    if (q == 0 && (f & 1u)) atomicOr(overflow_any, 1);
+    if ((f >> 1) != shape) {
+      s_bad = 1;
+      if (q == 0) atomicOr(overflow_any, 2);
+    }
+  }
+  __syncthreads();
+  if (s_bad) {
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      out_s[(size_t)q * k + j] = VODB_NEG_FLT_MAX;
+      out_i[(size_t)q * k + j] = -1;
+    }
+    return;
   }
   const size_t plane = flag_word / 3;  // entries per plane of a slot: [3][plane] tagged words, then the flag word
   auto entry = [&](int i) -> const uint64_t* {
