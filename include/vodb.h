@@ -62,7 +62,9 @@ extern "C" {
  * multiplies the first X planes with X query terms. TENSOR_X3 reproduces the fp32 result within the fp32-exact
  * tolerance (1e-5 relative; measured <= 4e-6) 3-4x faster than VODB_MODE_EXACT.
  * Correction terms that are zero for the whole query batch (float32 queries that are exact in the store dtype) are
- * detected on the device and skipped: TENSOR_X2 / _X3 then cost what TENSOR costs and return the same bits. */
+ * detected on the device and skipped: TENSOR_X2 / _X3 then cost what TENSOR costs and return the same bits.
+ * Host-resident float32 queries are classified on the host (a few microseconds): when every value is representable in
+ * the 16-bit store dtype the call runs as VODB_MODE_TENSOR outright, on the one-term kernels. */
 
 /* error codes */
 #define VODB_OK 0

@@ -353,9 +353,16 @@ def test_empty_correction_terms_are_skipped_without_changing_results(dtype):
     for nq in (40, 100, 200):
         xq = round_to(rng.standard_normal((nq, 320), dtype=np.float32), dtype)
         s1, i1 = st.search(xq, 50, mode="tensor")
+        import torch
+
+        xq_dev = torch.from_numpy(xq).cuda()
         for mode in ("tensor2", "tensor3"):
-            s, i = st.search(xq, 50, mode=mode)
+            s, i = st.search(xq, 50, mode=mode)              # host queries: classified on the host (one-term kernels)
             assert np.array_equal(i, i1) and np.array_equal(s, s1), (nq, mode)
+            ds, di = st.search_device(xq_dev, 50, mode=mode)  # device queries: prepare_kernel's term masks decide
+            torch.cuda.synchronize()
+            assert not st.check_async()
+            assert np.array_equal(di.cpu().numpy(), i1) and np.array_equal(ds.cpu().numpy(), s1), (nq, mode, "device")
         xq[nq // 2] = rng.standard_normal(320, dtype=np.float32)       # not representable: corrections needed again
         s3, i3 = st.search(xq, 50, mode="tensor3")
         rs, ri = flat_ip.search(xb, xq, 50)

@@ -646,6 +646,33 @@ int upload_queries(vodb_store* s, const void* queries, int q_dtype, int q_on_dev
   return VODB_OK;
 }
 
+// Host-resident float32 queries that are exactly representable in a 16-bit store dtype (what a bf16 / fp16 encoder
+// hands over after widening, reference src/vod_ops/workflows/predict/compute.py:128-129) have empty correction terms:
+// the multi-term modes then return the same bits as VODB_MODE_TENSOR, which runs the faster one-term kernels. The
+// scan over the host buffer costs a few microseconds (49k floats at 64 x 768) and stops at the first counterexample.
+// Device-resident queries are classified on the device instead (prepare_kernel's term masks).
+int effective_mode(const vodb_store* s, const void* queries, int q_dtype, int q_on_device, int nq, int mode) {
+  if (q_on_device || q_dtype != VODB_F32 || (mode != VODB_MODE_TENSOR_X2 && mode != VODB_MODE_TENSOR_X3)) return mode;
+  if (s->dtype != VODB_BF16 && s->dtype != VODB_F16) return mode;
+  const uint32_t* bits = reinterpret_cast<const uint32_t*>(queries);
+  const size_t n = (size_t)nq * s->dim;
+  if (s->dtype == VODB_BF16) {
+    uint32_t low = 0;
+    for (size_t i = 0; i < n; i += 4096) {  // blocks: vectorisable OR, early exit between blocks
+      const size_t e = std::min(n, i + 4096);
+      for (size_t j = i; j < e; ++j) low |= bits[j] & 0xffffu;
+      if (low) return mode;
+    }
+    return VODB_MODE_TENSOR;
+  }
+  const float* q = reinterpret_cast<const float*>(queries);
+  for (size_t i = 0; i < n; ++i) {
+    const float back = vodb_f16_to_f32(vodb_f32_to_f16(q[i]));
+    if (vm_f2u(back) != bits[i]) return mode;
+  }
+  return VODB_MODE_TENSOR;
+}
+
 int check_search_args(vodb_store* s, const void* queries, int q_dtype, int nq, int k, int mode, const float* out_scores,
                       const int64_t* out_idx, const char* fn) {
   VODB_REQUIRE(s != nullptr, "%s: store is NULL", fn);
@@ -869,6 +896,7 @@ int vodb_search(vodb_store* s, const void* queries, int q_dtype, int q_on_device
   if (rc != VODB_OK) return rc;
   Workspace& w = s->ws;
   const void* q_dev = nullptr;
+  mode = effective_mode(s, queries, q_dtype, q_on_device, nq, mode);
   rc = upload_queries(s, queries, q_dtype, q_on_device, nq, st, &q_dev);
   if (rc != VODB_OK) return rc;
 
@@ -988,6 +1016,7 @@ int vodb_search_sharded(vodb_store* s, vodb_xchg* x, const void* queries, int q_
   if (rc != VODB_OK) return rc;
   Workspace& w = s->ws;
   const void* q_dev = nullptr;
+  mode = effective_mode(s, queries, q_dtype, q_on_device, nq, mode);
   rc = upload_queries(s, queries, q_dtype, q_on_device, nq, st, &q_dev);
   if (rc != VODB_OK) return rc;
 
@@ -1411,6 +1440,7 @@ int vodb_retrieve_sample(vodb_store* s, const void* queries, int q_dtype, int q_
   }
   char* d = w.chain_dev;
   const void* q_dev = nullptr;
+  mode = effective_mode(s, queries, q_dtype, q_on_device, nq, mode);
   rc = upload_queries(s, queries, q_dtype, q_on_device, nq, st, &q_dev);
   if (rc != VODB_OK) return rc;
   uint8_t* labels = nullptr;

@@ -1127,9 +1127,29 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream
   return VODB_OK;
 }
 
+// corpus stages left for the resident-query variant (0 = the CTA's half of the query tile does not leave >= 6 of them)
+template <int BN>
+int resident_stages(const vodb_store* s) {
+  using C = Tc2Config<BN, 1>;
+  const int kchunks = (s->dim + KC - 1) / KC;
+  const int st = std::min<int>(C::kMaxStagesRes, ((int)kSmemMax - (int)C::kExtra - kchunks * (int)C::kBBytes) / (int)C::kABytes);
+  return (resident_enabled() && st >= 6) ? st : 0;
+}
+
+// one-term scan of up to 128 queries: resident-query pair kernel when it fits, else the 1-CTA kernel
+template <int BN>
+int launch_one_term_small(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream_t stream) {
+  const int st = resident_stages<BN>(s);
+  if (st > 0) return launch_pair<BN, 1, true>(s, a, term_policy, stream, st);
+  return launch_pair<BN, 1>(s, a, term_policy, stream);
+}
+
 // multi-term scan of a 16-bit store on CTA pairs. Batches above 128 queries are launched twice — the wide one-term
 // kernel, which works only if the correction terms turn out empty on the device (float32 queries that are exact in
 // the store dtype), and the multi-term kernel, which works only if they do not: exactly one of them finds items.
+// (Up to 128 queries the multi-term kernel skips the empty terms itself: a second launch per segment costs as much as
+// the resident one-term kernel would gain, measured. Host-resident queries are classified on the host instead,
+// api.cu `queries_fit_store_dtype`.)
 template <int T>
 int launch_pair_terms(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
   if (a.nq <= 64) return launch_pair<64, T>(s, a, kTermAlways, stream);
@@ -1163,18 +1183,10 @@ int launch_score_tensor(vodb_store* s, const SegmentArgs& a, cudaStream_t stream
     if (a.planes == 2) return a.nq <= 64 ? launch_bn<64, 2, 2>(s, a, stream) : launch_bn<128, 2, 2>(s, a, stream);
     return a.nq <= 64 ? launch_bn<64, 3, 3>(s, a, stream) : launch_bn<128, 3, 3>(s, a, stream);
   }
-  if (a.terms == 1 && a.nq <= 128 && pair_kernel_enabled() && resident_enabled()) {
+  if (a.terms == 1 && a.nq <= 128 && pair_kernel_enabled()) {
     // resident-query pair kernel when the CTA's half of the query tile (all K chunks) leaves >= 6 corpus stages
-    const int kchunks = (s->dim + KC - 1) / KC;
-    if (a.nq <= 64) {
-      using C = Tc2Config<64, 1>;
-      const int st = std::min<int>(C::kMaxStagesRes, ((int)kSmemMax - (int)C::kExtra - kchunks * (int)C::kBBytes) / (int)C::kABytes);
-      if (st >= 6) return launch_pair<64, 1, true>(s, a, kTermAlways, stream, st);
-    } else {
-      using C = Tc2Config<128, 1>;
-      const int st = std::min<int>(C::kMaxStagesRes, ((int)kSmemMax - (int)C::kExtra - kchunks * (int)C::kBBytes) / (int)C::kABytes);
-      if (st >= 6) return launch_pair<128, 1, true>(s, a, kTermAlways, stream, st);
-    }
+    if (a.nq <= 64 && resident_stages<64>(s) > 0) return launch_one_term_small<64>(s, a, kTermAlways, stream);
+    if (a.nq > 64 && resident_stages<128>(s) > 0) return launch_one_term_small<128>(s, a, kTermAlways, stream);
   }
   if (use_pair_kernel(a)) return launch_pair<256, 1>(s, a, kTermAlways, stream);
   if (pair_kernel_enabled() && a.terms == 2) return launch_pair_terms<2>(s, a, stream);
