@@ -47,6 +47,7 @@ w("Files: `r02a_*` ncu of the 64-query scan of a 1.25M-row shard BEFORE the coun
   "lines after the exchange buffer became plane-major (fused and NCCL exchange, reference arm under torchrun), k = 1000 probe; "
   "`r02f_*` ncu raw page of the kernels beside the scan, launch list of a small-shard search; `r02g_bench.json` bench line of the "
   "final build (another box: 2.215 ms), `r02_compute_sanitizer.txt` memcheck / racecheck of the final build; "
+  "`r02k_*` probes of the power-cap steps inside a loop of identical searches and of the idle gap before a search; "
   "`r02j_bench.json` bench line after host-resident queries are classified on the host (e2e 2.44 ms next to a 2.22 ms device step on "
   "that box; 2.57-2.67 ms before), `r02j_test_multigpu_n2.log`; `r02h_*` ncu raw pages of the valley shapes (256 and 384 queries) and the A/B sweep of the dropped wide pair kernel; "
   "`r02_sass_opcodes.txt` opcode histogram of `libvodb.so`; `traffic.json` the DRAM-traffic ratios bench.py multiplies with.\n")
