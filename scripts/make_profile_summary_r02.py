@@ -246,6 +246,48 @@ if f.exists():
           "~11 us; now a 16384-row dump, one scan and two selects. At 8 GPUs the merge kernel (fused exchange) follows; a multi-rank command cannot be "
           "wrapped in ncu, so the 8-GPU step is the CUDA-event time of `r02e_bench_n8.json` (0.350 ms whole step, 0.303 ms in the scoring kernels).\n")
 
+# rank 0 of a two-rank search under ncu (single-pass collections only; rank 1 runs unprofiled beside it)
+import csv as _csv
+def _ncu_long(name):
+    f = P / name
+    if not f.exists():
+        return []
+    rows = list(_csv.reader(f.open()))
+    h = next((i for i, r in enumerate(rows) if r and r[0] == "ID"), None)
+    if h is None:
+        return []
+    hd = rows[h]
+    return [dict(zip(hd, r)) for r in rows[h + 1:] if len(r) == len(hd)]
+xl, xn = _ncu_long("r02k_xchg_launches_rank0_ncu.csv"), _ncu_long("r02k_xchg_nvlink_rank0_ncu.csv")
+if xl and xn:
+    ours = [r for r in xl if "vodb" in r["Kernel Name"] and "synth_fill" not in r["Kernel Name"]]
+    def short(nm):
+        import re as _re
+        m = _re.search(r"(\w+_kernel(?:<[^(]*?>)?)\(", nm)
+        return m.group(1) if m else nm[:40]
+    w("## Fused exchange, rank 0 of a 2-rank search under ncu (r02k_xchg_launches_rank0_ncu.csv, r02k_xchg_nvlink_rank0_ncu.csv; scripts/r02_ncu_exchange.sh)\n")
+    w("2 x 1.25M rows, 64 queries. Only rank 0's command line carries ncu and rank 1 enqueues its search 0.3 s earlier, so the words rank 0's merge waits for are "
+      "already there. Collections that need kernel replay (`--set full`) fail in a process with CUDA-IPC peer mappings (ncu: UnknownError); single-pass ones work.\n")
+    w("| search | kernel | us |\n|---|---|---|")
+    names = ["warm-up, top-100", "top-100", "top-1000"]
+    si = -1
+    for r in ours:
+        if "prepare_kernel" in r["Kernel Name"]:
+            si += 1
+        if si >= 1:
+            w(f"| {names[min(si, 2)]} | `{short(r['Kernel Name'])}` | {float(r['Metric Value']) / 1e3:.1f} |")
+    tx = {}
+    for r in xn:
+        tx.setdefault(r["ID"], {"k": short(r["Kernel Name"])})[r["Metric Name"]] = float(r["Metric Value"])
+    w("\nNVLink bytes per launch (`nvltx__bytes.sum` / `nvlrx__bytes.sum`, launches of the top-100 then the top-1000 search):\n")
+    w("| kernel | NVLink tx bytes | NVLink rx bytes |\n|---|---|---|")
+    for i in sorted(tx, key=int):
+        w(f"| `{tx[i]['k']}` | {tx[i].get('nvltx__bytes.sum', 0):.0f} | {tx[i].get('nvlrx__bytes.sum', 0):.0f} |")
+    w("\nThe final select is the only kernel that touches NVLink: 188 KB sent for the 64 x 100 x 3 tagged words (153.6 KB) it stores into the peer's gather buffer "
+      "(1.23x: 32-byte packet granularity + headers), 1.91 MB for top-1000 (1.536 MB of words); the merge kernel reads its own HBM only (0 bytes on the links), "
+      "and nothing flows back but acknowledgements. With the exchange the final select takes 25.1 us against 19.9 us without it (1-GPU list above), the merge 10.0 us "
+      "(30.8 us for 2 x 1000 entries per query).\n")
+
 mg, ing = line("r02g_multigpu_store_n2_probe.json"), line("r02g_ingest_probe.json")
 if mg and ing:
     w("## Single-process multi-GPU master and ingest (r02g_multigpu_store_n2_probe.json, r02g_ingest_probe.json)\n")
