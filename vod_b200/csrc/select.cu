@@ -32,7 +32,7 @@ struct UIdx<int64_t> { using type = uint64_t; };
 
 template <typename IdxT>
 struct SelectSmem {
-  int hist[256];
+  int hist[512];     // radix histogram; the thread-maximum bound uses both halves (one per pass)
   int bin;
   int need;
   int n_eq;
@@ -53,14 +53,14 @@ __device__ __forceinline__ bool before(uint32_t oa, U ia, uint32_t ob, U ib) {
 // bottom: lane l owns 8 consecutive bins in scan order, a warp prefix sum over the lane totals finds the lane, the
 // lane walks its 8 bins. Writes sm.bin, sm.need (rank inside the bin, 1-based) and sm.n_eq (size of the bin).
 template <bool kDescending, typename IdxT>
-__device__ __forceinline__ void find_bin(SelectSmem<IdxT>& sm, int need, int lane) {
+__device__ __forceinline__ void find_bin(const int* hist, SelectSmem<IdxT>& sm, int need, int lane) {
   int h[8];
   int total = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int pos = lane * 8 + j;  // position in scan order
     const int bin = kDescending ? 255 - pos : pos;
-    h[j] = sm.hist[bin];
+    h[j] = hist[bin];
     total += h[j];
   }
   int incl = total;
@@ -90,15 +90,26 @@ __device__ __forceinline__ void find_bin(SelectSmem<IdxT>& sm, int need, int lan
 // (sorted if do_sort), returns n_sel = min(n,k); *vstar_out = ord image of the k-th best score (0 if n < k).
 // `cache` (optional, capacity cache_n >= n required to be used) keeps the ordered score images in shared memory
 // after the first pass, so that the remaining radix passes and the compaction never go back to L2.
+//
+// Thread-maximum bound (surv_o / surv_i given, 2k <= threads, keys cheap to re-read: cached or `smem_src`): every
+// thread keeps the maximum of the keys it read in the first sweep. The k-th largest of those `threads` maxima is a
+// lower bound of the k-th best key of the list (k different entries reach it), and a tight one: for a list in random
+// order about -threads * ln(1 - k/threads) entries pass it whatever the list length (115 of a 16384-entry list at
+// k = 100 with 1024 threads). The bound is found with two 8-bit radix passes over ONE value per thread (its low 16 bits
+// are left zero: ~5% more survivors), the survivors are compacted and rank-sorted, and the first k are the result —
+// seven block barriers and two sweeps instead of the ~20 barriers and six sweeps of the radix select below, which stays
+// as the general path (k > threads/2, or an ordering of the list that leaves more than `threads` survivors).
 template <typename IdxT, typename LoadS, typename LoadI>
 __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_sort, SelectSmem<IdxT>& sm,
                             uint32_t* sel_o, IdxT* sel_i, int P, uint32_t* cache, int cache_n, uint32_t* vstar_out,
-                            const float* flat_s = nullptr) {
+                            const float* flat_s = nullptr, uint32_t* surv_o = nullptr, IdxT* surv_i = nullptr,
+                            bool smem_src = false) {
   using U = typename UIdx<IdxT>::type;
   const int tid = threadIdx.x;
   const int nt = blockDim.x;
   int n_sel;
   uint32_t vstar = 0u;
+  bool sorted = false;  // the selection below already left sel_o / sel_i in output order
   const bool cached = cache != nullptr && n <= cache_n;
   auto key = [&](int i) -> uint32_t { return cached ? cache[i] : ord_u32(load_s(i)); };
 
@@ -117,20 +128,10 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
     n_sel = n;
     vstar = (n == k && n > 0) ? sm.min_ord : 0u;
   } else {
-    uint32_t prefix = 0u, mask = 0u;
-    int need = k;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      for (int t = tid; t < 256; t += nt) sm.hist[t] = 0;
-      __syncthreads();
-      if (shift == 24) {
-        // First pass. A histogram of the top byte (sign + 7 exponent bits) would send most of the list to three or
-        // four bins, and shared-memory atomics on one address cost a cycle per lane: ~8 us for a 16k-entry dump
-        // list. Scores of one query nearly always have >= k entries in the top byte of their maximum, so the pass
-        // first tries exactly that bin with ballots instead of atomics: (a) read the scores (4 independent loads in
-        // flight per thread), cache the ordered images, reduce the maximum; (b) count the entries that share the
-        // maximum's top byte. If there are at least `need` of them the k-th best lies in that bin and the pass is
-        // done; otherwise (top bin too small, e.g. one outlier score) the general histogram below runs.
-        uint32_t lmax = 0u;
+    // First sweep: read the scores (4 independent loads in flight per thread), cache the ordered images, keep the
+    // thread's maximum.
+    uint32_t lmax = 0u;
+    {
         int i = tid;
         if (flat_s != nullptr && cached && ((reinterpret_cast<uintptr_t>(flat_s) | reinterpret_cast<uintptr_t>(cache)) & 15) == 0) {
           // contiguous list (16-byte aligned): four 16-byte loads in flight per thread, 16 scores each round — the
@@ -168,6 +169,89 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
           if (cached) cache[i] = o;
           lmax = max(lmax, o);
         }
+    }
+    if (surv_o != nullptr && (cached || smem_src) && 2 * k <= nt) {
+      for (int t = tid; t < 512; t += nt) sm.hist[t] = 0;
+      if (tid == 0) sm.sel_count = 0;
+      __syncthreads();  // also publishes the cached keys
+      const int lane = tid & 31;
+      {  // pass A: top byte of the thread maxima (equal bins of a warp share one atomic)
+        const uint32_t b = lmax >> 24;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        if (lane == __ffs(peers) - 1) atomicAdd(&sm.hist[b], __popc(peers));
+      }
+      __syncthreads();
+      if (tid < 32) find_bin<true>(sm.hist, sm, k, tid);
+      __syncthreads();
+      const uint32_t bin_a = (uint32_t)sm.bin;
+      const int need_b = sm.need;
+      {  // pass B: second byte, among the maxima inside bin A
+        const bool in = (lmax >> 24) == bin_a;
+        const uint32_t b = in ? ((lmax >> 16) & 255u) : 256u;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        if (in && lane == __ffs(peers) - 1) atomicAdd(&sm.hist[256 + b], __popc(peers));
+      }
+      __syncthreads();
+      if (tid < 32) find_bin<true>(sm.hist + 256, sm, need_b, tid);
+      __syncthreads();
+      const uint32_t bound = (bin_a << 24) | ((uint32_t)sm.bin << 16);
+      // compaction: key and list POSITION of every survivor (the id is fetched afterwards, one load per survivor and
+      // all of them in flight together: loading it here would serialise an L2 round trip per survivor of a thread)
+      for (int i = tid; i < n; i += nt) {
+        const uint32_t o = key(i);
+        if (o >= bound) {
+          const int pos = atomicAdd(&sm.sel_count, 1);
+          if (pos < nt) {
+            surv_o[pos] = o;
+            surv_i[pos] = (IdxT)i;
+          }
+        }
+      }
+      __syncthreads();
+      const int ns = sm.sel_count;  // >= k: the k largest thread maxima are different entries
+      if (ns <= nt) {
+        if (tid < ns) surv_i[tid] = load_i((int)surv_i[tid]);  // own slot only
+        __syncthreads();
+        // rank among the survivors = output position ((score desc, id asc), position for the merges' equal padding);
+        // g threads share one survivor's comparisons (g consecutive lanes, g | 32)
+        const int g = (ns * 8 <= nt) ? 8 : (ns * 4 <= nt) ? 4 : (ns * 2 <= nt) ? 2 : 1;
+        const int sv = tid / g, part = tid - sv * g;
+        const bool live = sv < ns;
+        const uint32_t o = live ? surv_o[sv] : 0u;
+        const U id = live ? (U)surv_i[sv] : (U)0;
+        int rank = 0;
+        if (live) {
+#pragma unroll 4
+          for (int j = part; j < ns; j += g) {
+            const uint32_t oj = surv_o[j];
+            const U ij = (U)surv_i[j];
+            rank += (before<U>(oj, ij, o, id) || (oj == o && ij == id && j < sv)) ? 1 : 0;
+          }
+        }
+        for (int off = g >> 1; off > 0; off >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, off);
+        if (live && part == 0 && rank < k) {
+          sel_o[rank] = o;
+          sel_i[rank] = (IdxT)id;
+        }
+        __syncthreads();
+        sorted = true;
+        n_sel = k;
+        vstar = sel_o[k - 1];
+      }
+    }
+    if (!sorted) {
+    uint32_t prefix = 0u, mask = 0u;
+    int need = k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int t = tid; t < 256; t += nt) sm.hist[t] = 0;
+      __syncthreads();
+      if (shift == 24) {
+        // First radix pass. A histogram of the top byte (sign + 7 exponent bits) would send most of the list to three
+        // or four bins, and shared-memory atomics on one address cost a cycle per lane: ~8 us for a 16k-entry dump
+        // list. Scores of one query nearly always have >= k entries in the top byte of their maximum, so the pass
+        // first tries exactly that bin with ballots instead of atomics: reduce the maximum, count the entries that
+        // share its top byte. If there are at least `need` of them the k-th best lies in that bin and the pass is
+        // done; otherwise (top bin too small, e.g. one outlier score) the general histogram below runs.
         if (tid == 0) { sm.max_ord = 0u; sm.n_top = 0; }
         __syncthreads();
         lmax = __reduce_max_sync(0xffffffffu, lmax);
@@ -195,7 +279,7 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
         }
       }
       __syncthreads();
-      if (tid < 32) find_bin<true>(sm, need, tid);
+      if (tid < 32) find_bin<true>(sm.hist, sm, need, tid);
       __syncthreads();
       prefix |= (uint32_t)sm.bin << shift;
       mask |= 0xffu << shift;
@@ -220,7 +304,7 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
           }
         }
         __syncthreads();
-        if (tid < 32) find_bin<false>(sm, ineed, tid);
+        if (tid < 32) find_bin<false>(sm.hist, sm, ineed, tid);
         __syncthreads();
         iprefix |= (U)sm.bin << shift;
         imask |= (U)0xff << shift;
@@ -254,9 +338,12 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
     }
     __syncthreads();
     n_sel = min(sm.sel_count, k);
+    }  // !sorted
   }
 
-  if (do_sort && n_sel <= nt) {
+  if (sorted) {
+    // nothing to do
+  } else if (do_sort && n_sel <= nt) {
     // Rank sort: with at most one selected entry per thread, entry i goes to position #{j : j before i} — the order
     // is total (ids are unique within a list; equal padding entries are ordered by position), so the ranks are a permutation. One pass of n_sel broadcast reads per
     // thread and two barriers, against log2(P)*(log2(P)+1)/2 barrier-separated stages of a bitonic network.
@@ -313,17 +400,19 @@ __host__ __device__ inline int pow2ceil(int x) {
   return p;
 }
 
-// dynamic smem layout: sel_o[P] | sel_i[P]
+// dynamic smem layout: sel_i[P] | sel_o[P] | cache[cache_n] | (fast) surv_o[threads] | surv_i[threads]
 template <typename IdxT>
 __global__ void __launch_bounds__(1024)
 select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __restrict__ cnt, float* __restrict__ tau,
               int cap, int k, int P, int final_pass, float* __restrict__ out_s, int64_t* __restrict__ out_i,
-              int64_t row_offset, const ExchangeDst xd, int use_xd, int cache_n) {
+              int64_t row_offset, const ExchangeDst xd, int use_xd, int cache_n, int fast) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ SelectSmem<int32_t> sm;
   int32_t* sel_i = reinterpret_cast<int32_t*>(dyn);
   uint32_t* sel_o = reinterpret_cast<uint32_t*>(dyn + (size_t)P * sizeof(int32_t));
   uint32_t* cache = cache_n > 0 ? sel_o + P : nullptr;
+  uint32_t* surv_o = fast ? sel_o + P + cache_n : nullptr;  // survivors of the thread-maximum bound (block_select)
+  int32_t* surv_i = fast ? reinterpret_cast<int32_t*>(surv_o + blockDim.x) : nullptr;
   const int q = blockIdx.x;
   pdl_launch_dependents();
   pdl_wait();  // the scoring kernel's appends must be complete and visible
@@ -334,7 +423,8 @@ select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __r
   auto load_i = [&](int i) -> int32_t { return li[i]; };
   uint32_t vstar;
   // lists start at multiples of cap (>= 2048) floats: 16-byte aligned for the vectorised first pass
-  int n_sel = block_select<int32_t>(load_s, load_i, n, k, final_pass != 0, sm, sel_o, sel_i, P, cache, cache_n, &vstar, ls);
+  int n_sel = block_select<int32_t>(load_s, load_i, n, k, final_pass != 0, sm, sel_o, sel_i, P, cache, cache_n, &vstar, ls,
+                                    surv_o, surv_i);
   __syncthreads();
   if (final_pass && use_xd) {
     // fused exchange: store this shard's result into every rank's gather buffer (own rank included) as
@@ -391,7 +481,7 @@ select_kernel(float* __restrict__ cand_s, int32_t* __restrict__ cand_i, int* __r
 // (world*k_in*12 bytes > ~190 KB): every pass then re-reads global memory as the first version did.
 __global__ void __launch_bounds__(1024)
 merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, int n_lists, int nq, int k_in,
-             int k_out, int P, int staged, float* __restrict__ out_s, int64_t* __restrict__ out_i) {
+             int k_out, int P, int staged, int fast, float* __restrict__ out_s, int64_t* __restrict__ out_i) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ SelectSmem<int64_t> sm;
   int64_t* sel_i = reinterpret_cast<int64_t*>(dyn);
@@ -415,7 +505,10 @@ merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, 
     __syncthreads();
     auto load_s = [&](int i) -> float { return all_s[i]; };
     auto load_i = [&](int i) -> int64_t { return all_i[i]; };
-    n_sel = block_select<int64_t>(load_s, load_i, n, k_out, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar);
+    int64_t* surv_i = fast ? all_i + n + (n + 1) / 2 : nullptr;  // behind all_s, 8-byte aligned
+    uint32_t* surv_o = fast ? reinterpret_cast<uint32_t*>(surv_i + blockDim.x) : nullptr;
+    n_sel = block_select<int64_t>(load_s, load_i, n, k_out, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar, nullptr, surv_o,
+                                  surv_i, true);
   } else {
     auto load_s = [&](int i) -> float { return scores[off_of(i)]; };
     auto load_i = [&](int i) -> int64_t { return idx[off_of(i)]; };
@@ -446,7 +539,7 @@ __device__ __forceinline__ uint64_t ll_wait_word(const uint64_t* p, uint32_t epo
 
 __global__ void __launch_bounds__(1024)
 merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, int world, size_t slot_words,
-                      size_t flag_word, int nq, int k, int P, int staged, float* __restrict__ out_s,
+                      size_t flag_word, int nq, int k, int P, int staged, int fast, float* __restrict__ out_s,
                       int64_t* __restrict__ out_i, int* __restrict__ overflow_any) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ SelectSmem<int64_t> sm;
@@ -506,7 +599,10 @@ merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, in
     __syncthreads();
     auto load_s = [&](int i) -> float { return all_s[i]; };
     auto load_i = [&](int i) -> int64_t { return all_i[i]; };
-    n_sel = block_select<int64_t>(load_s, load_i, n, k, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar);
+    int64_t* surv_i = fast ? all_i + n + (n + 1) / 2 : nullptr;  // behind all_s, 8-byte aligned
+    uint32_t* surv_o = fast ? reinterpret_cast<uint32_t*>(surv_i + blockDim.x) : nullptr;
+    n_sel = block_select<int64_t>(load_s, load_i, n, k, true, sm, sel_o, sel_i, P, nullptr, 0, &vstar, nullptr, surv_o,
+                                  surv_i, true);
   } else {
     auto load_s = [&](int i) -> float { return __uint_as_float((uint32_t)ll_wait_word(entry(i), epoch)); };
     auto load_i = [&](int i) -> int64_t {
@@ -522,6 +618,12 @@ merge_exchange_kernel(const uint64_t* __restrict__ gather_ll, uint32_t epoch, in
     out_s[(size_t)q * k + j] = ok ? ord_to_float(sel_o[j]) : VODB_NEG_FLT_MAX;
     out_i[(size_t)q * k + j] = ok ? sel_i[j] : -1;
   }
+}
+
+// VODB_FAST_SELECT=0 keeps every selection on the radix path (A/B comparisons, tests of the general path)
+inline bool fast_select_enabled() {
+  static const char* env = std::getenv("VODB_FAST_SELECT");
+  return env ? (env[0] != '0') : true;
 }
 
 inline int threads_for(int n) {
@@ -540,44 +642,48 @@ int launch_select(float* cand_s, int32_t* cand_i, int* cnt, float* tau, int cap,
   // row count, or a few multiples of k afterwards); longer lists fall back to re-reading L2 on every pass
   int cache_n = std::min(std::max(expected_n, 0), std::min(cap, 32768));
   cache_n = (cache_n + 255) / 256 * 256;
-  size_t smem = (size_t)P * (sizeof(int32_t) + sizeof(uint32_t)) + (size_t)cache_n * sizeof(uint32_t);
-  if (smem > 48 * 1024) VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&select_kernel<int32_t>), 160 * 1024));
-  ExchangeDst none{};
-  // few queries: threads by list length (long lists want memory-level parallelism, short ones cheap barriers — a
-  // select is ~60 block barriers); many queries: small CTAs, several per SM
+  // few queries: threads by list length (long lists want memory-level parallelism, short ones cheap barriers);
+  // many queries: small CTAs, several per SM
   const int threads = (nq > 512) ? kSelThreads : threads_for(expected_n > 0 ? expected_n : cap);
+  const int fast = fast_select_enabled() && 2 * k <= threads ? 1 : 0;  // thread-maximum bound (block_select)
+  size_t smem = (size_t)P * (sizeof(int32_t) + sizeof(uint32_t)) + (size_t)cache_n * sizeof(uint32_t) +
+                (fast ? (size_t)threads * (sizeof(uint32_t) + sizeof(int32_t)) : 0);
+  if (smem > 48 * 1024) VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&select_kernel<int32_t>), 170 * 1024));
+  ExchangeDst none{};
   VODB_CUDA_CHECK(launch_pdl(select_kernel<int32_t>, dim3(nq), dim3(threads), smem, stream, cand_s, cand_i, cnt, tau, cap,
                              k, P, final_pass ? 1 : 0, out_s, out_i, row_offset, xd ? *xd : none,
-                             (xd && final_pass) ? 1 : 0, cache_n));
+                             (xd && final_pass) ? 1 : 0, cache_n, fast));
   return VODB_OK;
 }
 
 // dynamic shared memory of the merge kernels: selection buffers [P] + (if it fits) the staged world*k entries
-static size_t merge_smem(int P, int n, int* staged) {
+// (+ the survivor buffers of the thread-maximum bound when it applies: staged input, 2k <= threads)
+static size_t merge_smem(int P, int n, int k, int threads, int* staged, int* fast) {
   const size_t sel = ((size_t)P * (sizeof(int64_t) + sizeof(uint32_t)) + 15) & ~(size_t)15;
-  const size_t all = (size_t)n * (sizeof(int64_t) + sizeof(float));
-  *staged = (sel + all <= 190 * 1024) ? 1 : 0;
-  return *staged ? sel + all : sel;
+  const size_t all = (size_t)n * sizeof(int64_t) + (size_t)(n + 1) / 2 * 2 * sizeof(float);
+  *staged = (sel + all <= 180 * 1024) ? 1 : 0;
+  *fast = (*staged && fast_select_enabled() && 2 * k <= threads) ? 1 : 0;
+  return (*staged ? sel + all : sel) + (*fast ? (size_t)threads * (sizeof(int64_t) + sizeof(uint32_t)) : 0);
 }
 
 int launch_merge_exchange(const uint64_t* gather_ll, uint32_t epoch, int world, size_t slot_words, size_t flag_word, int nq,
                           int k, float* out_s, int64_t* out_i, int* overflow_any, cudaStream_t stream) {
-  int P = pow2ceil(k), staged = 0;
-  const size_t smem = merge_smem(P, world * k, &staged);
-  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&merge_exchange_kernel), smem));
+  int P = pow2ceil(k), staged = 0, fast = 0;
   const int threads = (nq > 512) ? kSelThreads : threads_for(world * k);
+  const size_t smem = merge_smem(P, world * k, k, threads, &staged, &fast);
+  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&merge_exchange_kernel), smem));
   VODB_CUDA_CHECK(launch_pdl(merge_exchange_kernel, dim3(nq), dim3(threads), smem, stream, gather_ll, epoch, world,
-                             slot_words, flag_word, nq, k, P, staged, out_s, out_i, overflow_any));
+                             slot_words, flag_word, nq, k, P, staged, fast, out_s, out_i, overflow_any));
   return VODB_OK;
 }
 
 int launch_merge(const float* scores, const int64_t* idx, int n_lists, int nq, int k_in, int k_out, float* out_s,
                  int64_t* out_i, cudaStream_t stream) {
-  int P = pow2ceil(k_out), staged = 0;
-  const size_t smem = merge_smem(P, n_lists * k_in, &staged);
-  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&merge_kernel), smem));
+  int P = pow2ceil(k_out), staged = 0, fast = 0;
   const int threads = (nq > 512) ? kSelThreads : threads_for(n_lists * k_in);
-  merge_kernel<<<nq, threads, smem, stream>>>(scores, idx, n_lists, nq, k_in, k_out, P, staged, out_s, out_i);
+  const size_t smem = merge_smem(P, n_lists * k_in, k_out, threads, &staged, &fast);
+  VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&merge_kernel), smem));
+  merge_kernel<<<nq, threads, smem, stream>>>(scores, idx, n_lists, nq, k_in, k_out, P, staged, fast, out_s, out_i);
   VODB_CUDA_CHECK(cudaGetLastError());
   return VODB_OK;
 }
