@@ -1,10 +1,12 @@
-// select.cu — per-query exact top-k selection over candidate lists (radix select + bitonic sort).
+// select.cu — per-query exact top-k selection over candidate lists (thread-maximum bound + rank sort, radix select +
+// bitonic sort as the general path).
 //
 // Replaces the k-selection half of faiss' IndexFlat::search (heap / reservoir collection behind
 // `faiss_index.search`, reference src/vod_search/faiss_search/server.py:84) and, as `merge`, the
 // host-side IndexShards merge behind `faiss.index_cpu_to_all_gpus(..., co.shard=True)` (server.py:51-54).
 //
-// One CTA per query. The list is a bag of (score, id) pairs appended by the scoring kernels.
+// One CTA per query. The list is a bag of (score, id) pairs appended by the scoring kernels. Fast path: see
+// block_select (k <= threads/2). General path:
 //   1. 4-pass (8 bits each) MSB radix select on the order-preserving uint32 image of the score finds
 //      v* = the k-th largest score and how many entries tied at v* are needed;
 //   2. if the tie group is larger than needed, a second radix select picks the smallest ids;
