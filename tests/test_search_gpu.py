@@ -48,6 +48,26 @@ def test_exact_mode_bit_exact_on_integer_data(dtype, n, d, nq, k):
     st.close()
 
 
+@pytest.mark.parametrize("nq", [7, 600])
+@pytest.mark.parametrize("k", [100, 127, 128, 129, 192, 256, 257, 384, 385, 511, 512, 513, 1000])
+def test_selection_paths_bit_exact(nq, k):
+    """Every selection path of `block_select` against the oracle: thread-maximum bound + rank sort (2k <= CTA size:
+    1024 threads for the few-query lists, 256 for many queries), radix select + rank sort (<= 384 selected), radix
+    select + bitonic sort. Integers in [-100, 100] are exact in bf16 and their 64-term dot products (< 2^24) exact in
+    fp32, and with scores spread over +-640000 ties are rare, so the bound really filters (the +-3 data of the tests
+    above ties so often that most of its lists fall through to the radix path)."""
+    rng = np.random.default_rng(1000 * nq + k)
+    xb = rng.integers(-100, 101, size=(30_000, 64)).astype(np.float32)
+    xq = rng.integers(-100, 101, size=(nq, 64)).astype(np.float32)
+    st = _store(xb, "bfloat16")
+    s, i = st.search(xq, k, mode="tensor")
+    rs, ri = flat_ip.search(xb, xq, k)
+    assert np.array_equal(i, ri)
+    assert np.array_equal(s, rs)
+    assert st.stats()["safe_fallback"] == 0
+    st.close()
+
+
 @pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
 @pytest.mark.parametrize("n,d,nq,k", [(1, 8, 1, 1), (130, 64, 5, 100), (1000, 130, 64, 7), (5000, 768, 65, 100),
                                       (40000, 96, 129, 100), (70000, 768, 300, 1000), (300_000, 64, 9, 10)])

@@ -88,6 +88,40 @@ __device__ __forceinline__ void find_bin(const int* hist, SelectSmem<IdxT>& sm, 
   }
 }
 
+// Rank sort of ns <= blockDim.x entries: entry i goes to position #{j : j before i} in (score desc, id asc) order; equal
+// (score, id) pairs exist only as padding entries of the merges and are ordered by position, so the ranks are a
+// permutation. g consecutive lanes (g | 32) share one entry's ns comparisons. Entries ranked below k_out are dropped.
+// One pass of broadcast shared-memory reads and one or two barriers, against log2(P)*(log2(P)+1)/2 barrier-separated
+// stages of a bitonic network — but ns^2 comparisons: the callers use it up to kRankSortMax entries.
+constexpr int kRankSortMax = 384;
+template <typename IdxT>
+__device__ __forceinline__ void rank_sort(const uint32_t* src_o, const IdxT* src_i, int ns, int k_out, uint32_t* dst_o,
+                                          IdxT* dst_i, bool in_place) {
+  using U = typename UIdx<IdxT>::type;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int g = (ns * 8 <= nt) ? 8 : (ns * 4 <= nt) ? 4 : (ns * 2 <= nt) ? 2 : 1;
+  const int sv = tid / g, part = tid - sv * g;
+  const bool live = sv < ns;
+  const uint32_t o = live ? src_o[sv] : 0u;
+  const U id = live ? (U)src_i[sv] : (U)0;
+  int rank = 0;
+  if (live) {
+#pragma unroll 4
+    for (int j = part; j < ns; j += g) {
+      const uint32_t oj = src_o[j];
+      const U ij = (U)src_i[j];
+      rank += (before<U>(oj, ij, o, id) || (oj == o && ij == id && j < sv)) ? 1 : 0;
+    }
+  }
+  for (int off = g >> 1; off > 0; off >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, off);
+  if (in_place) __syncthreads();
+  if (live && part == 0 && rank < k_out) {
+    dst_o[rank] = o;
+    dst_i[rank] = (IdxT)id;
+  }
+  __syncthreads();
+}
+
 // Core routine. load_s(i) / load_i(i) read entry i in [0,n). Results: sel_o/sel_i[0..n_sel) in shared memory
 // (sorted if do_sort), returns n_sel = min(n,k); *vstar_out = ord image of the k-th best score (0 if n < k).
 // `cache` (optional, capacity cache_n >= n required to be used) keeps the ordered score images in shared memory
@@ -214,28 +248,7 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
       if (ns <= nt) {
         if (tid < ns) surv_i[tid] = load_i((int)surv_i[tid]);  // own slot only
         __syncthreads();
-        // rank among the survivors = output position ((score desc, id asc), position for the merges' equal padding);
-        // g threads share one survivor's comparisons (g consecutive lanes, g | 32)
-        const int g = (ns * 8 <= nt) ? 8 : (ns * 4 <= nt) ? 4 : (ns * 2 <= nt) ? 2 : 1;
-        const int sv = tid / g, part = tid - sv * g;
-        const bool live = sv < ns;
-        const uint32_t o = live ? surv_o[sv] : 0u;
-        const U id = live ? (U)surv_i[sv] : (U)0;
-        int rank = 0;
-        if (live) {
-#pragma unroll 4
-          for (int j = part; j < ns; j += g) {
-            const uint32_t oj = surv_o[j];
-            const U ij = (U)surv_i[j];
-            rank += (before<U>(oj, ij, o, id) || (oj == o && ij == id && j < sv)) ? 1 : 0;
-          }
-        }
-        for (int off = g >> 1; off > 0; off >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, off);
-        if (live && part == 0 && rank < k) {
-          sel_o[rank] = o;
-          sel_i[rank] = (IdxT)id;
-        }
-        __syncthreads();
+        rank_sort<IdxT>(surv_o, surv_i, ns, k, sel_o, sel_i, false);  // the first k, in output order
         sorted = true;
         n_sel = k;
         vstar = sel_o[k - 1];
@@ -345,29 +358,8 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
 
   if (sorted) {
     // nothing to do
-  } else if (do_sort && n_sel <= nt) {
-    // Rank sort: with at most one selected entry per thread, entry i goes to position #{j : j before i} — the order
-    // is total (ids are unique within a list; equal padding entries are ordered by position), so the ranks are a permutation. One pass of n_sel broadcast reads per
-    // thread and two barriers, against log2(P)*(log2(P)+1)/2 barrier-separated stages of a bitonic network.
-    uint32_t o = 0u;
-    U id = 0;
-    int rank = 0;
-    if (tid < n_sel) {
-      o = sel_o[tid];
-      id = (U)sel_i[tid];
-      for (int j = 0; j < n_sel; ++j) {
-        const uint32_t oj = sel_o[j];
-        const U ij = (U)sel_i[j];
-        // identical (score, id) pairs exist only as padding entries of the merges; their position breaks the tie
-        rank += (before<U>(oj, ij, o, id) || (oj == o && ij == id && j < tid)) ? 1 : 0;
-      }
-    }
-    __syncthreads();
-    if (tid < n_sel) {
-      sel_o[rank] = o;
-      sel_i[rank] = (IdxT)id;
-    }
-    __syncthreads();
+  } else if (do_sort && n_sel <= nt && n_sel <= kRankSortMax) {
+    rank_sort<IdxT>(sel_o, sel_i, n_sel, n_sel, sel_o, sel_i, true);
   } else if (do_sort) {
     for (int i = n_sel + tid; i < P; i += nt) {  // padding sorts last
       sel_o[i] = 0u;
