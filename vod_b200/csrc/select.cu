@@ -88,6 +88,40 @@ __device__ __forceinline__ void find_bin(const int* hist, SelectSmem<IdxT>& sm, 
   }
 }
 
+// The same search done by EVERY warp for itself (descending), result in registers: no shared-memory hand-over and no
+// barrier after it — the thread-maximum bound runs it twice on a 32-warp CTA whose other warps would only wait.
+__device__ __forceinline__ void find_bin_every_warp(const int* hist, int need, int lane, int& bin_out, int& need_out) {
+  // scan position p = j * 32 + lane (bin 255 - p): eight conflict-free loads; block j = 32 consecutive positions
+  int v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = hist[255 - (j * 32 + lane)];
+  int cum = 0, jb = 7, before = 0;
+  bool found = false;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int t = __reduce_add_sync(0xffffffffu, v[j]);
+    if (!found && (cum + t >= need || j == 7)) {
+      found = true;
+      jb = j;
+      before = cum;
+    }
+    cum += t;
+  }
+  int x = v[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) x = (j == jb) ? v[j] : x;
+  int incl = x;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += u;
+  }
+  const unsigned hit = __ballot_sync(0xffffffffu, before + incl >= need);
+  const int owner = hit ? (__ffs(hit) - 1) : 31;
+  bin_out = 255 - (jb * 32 + owner);
+  need_out = need - (before + __shfl_sync(0xffffffffu, incl - x, owner));
+}
+
 // Rank sort of ns <= blockDim.x entries: entry i goes to position #{j : j before i} in (score desc, id asc) order; equal
 // (score, id) pairs exist only as padding entries of the merges and are ordered by position, so the ranks are a
 // permutation. g consecutive lanes (g | 32) share one entry's ns comparisons. Entries ranked below k_out are dropped.
@@ -133,7 +167,7 @@ __device__ __forceinline__ void rank_sort(const uint32_t* src_o, const IdxT* src
 // order about -threads * ln(1 - k/threads) entries pass it whatever the list length (115 of a 16384-entry list at
 // k = 100 with 1024 threads). The bound is found with two 8-bit radix passes over ONE value per thread (its low 16 bits
 // are left zero: ~5% more survivors), the survivors are compacted and rank-sorted, and the first k are the result —
-// seven block barriers and two sweeps instead of the ~20 barriers and six sweeps of the radix select below, which stays
+// six block barriers and two sweeps instead of the ~20 barriers and six sweeps of the radix select below, which stays
 // as the general path (k > threads/2, or an ordering of the list that leaves more than `threads` survivors).
 template <typename IdxT, typename LoadS, typename LoadI>
 __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_sort, SelectSmem<IdxT>& sm,
@@ -217,10 +251,9 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
         if (lane == __ffs(peers) - 1) atomicAdd(&sm.hist[b], __popc(peers));
       }
       __syncthreads();
-      if (tid < 32) find_bin<true>(sm.hist, sm, k, tid);
-      __syncthreads();
-      const uint32_t bin_a = (uint32_t)sm.bin;
-      const int need_b = sm.need;
+      int bin_a_i, need_b;
+      find_bin_every_warp(sm.hist, k, lane, bin_a_i, need_b);
+      const uint32_t bin_a = (uint32_t)bin_a_i;
       {  // pass B: second byte, among the maxima inside bin A
         const bool in = (lmax >> 24) == bin_a;
         const uint32_t b = in ? ((lmax >> 16) & 255u) : 256u;
@@ -228,9 +261,9 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
         if (in && lane == __ffs(peers) - 1) atomicAdd(&sm.hist[256 + b], __popc(peers));
       }
       __syncthreads();
-      if (tid < 32) find_bin<true>(sm.hist + 256, sm, need_b, tid);
-      __syncthreads();
-      const uint32_t bound = (bin_a << 24) | ((uint32_t)sm.bin << 16);
+      int bin_b, need_c;
+      find_bin_every_warp(sm.hist + 256, need_b, lane, bin_b, need_c);
+      const uint32_t bound = (bin_a << 24) | ((uint32_t)bin_b << 16);
       // compaction: key and list POSITION of every survivor (the id is fetched afterwards, one load per survivor and
       // all of them in flight together: loading it here would serialise an L2 round trip per survivor of a thread)
       for (int i = tid; i < n; i += nt) {
