@@ -48,6 +48,8 @@ w("Files: `r02a_*` ncu of the 64-query scan of a 1.25M-row shard BEFORE the coun
   "`r02f_*` ncu raw page of the kernels beside the scan, launch list of a small-shard search; `r02g_bench.json` bench line of the "
   "final build (another box: 2.215 ms), `r02_compute_sanitizer.txt` memcheck / racecheck of the final build; "
   "`r02k_*` probes of the power-cap steps inside a loop of identical searches and of the idle gap before a search; "
+  "`r02l_*` the thread-maximum selection: A/B of the select time, ncu raw page of its first version, bench lines of the final build at 1 / 2 / 8 GPUs "
+  "(8 GPUs without the target-shape and 8192-query sections), k = 1000 probe, 2-GPU test log; "
   "`r02j_bench.json` bench line after host-resident queries are classified on the host (e2e 2.44 ms next to a 2.22 ms device step on "
   "that box; 2.57-2.67 ms before), `r02j_test_multigpu_n2.log`; `r02h_*` ncu raw pages of the valley shapes (256 and 384 queries) and the A/B sweep of the dropped wide pair kernel; "
   "`r02_sass_opcodes.txt` opcode histogram of `libvodb.so`; `traffic.json` the DRAM-traffic ratios bench.py multiplies with.\n")
@@ -111,6 +113,25 @@ for n in (2, 4, 8):
     w(f"Target shape at {n} GPUs (`r02i_scale_n{n}.json` -> `target_config`; parity ok = {t['parity']['ok']}): " + "; ".join(
         f"top-{run['top_k']} x {run['queries_per_batch']} q: {run['ms_per_step']:.2f} ms = {100 * run['whole_step_frac']:.1f}% (target {100 * run['target_whole_step_frac']:.0f}%)"
         for run in t["runs"]) + "\n")
+
+# final build (thread-maximum selection)
+fl = [(n, line(f)) for n, f in ((1, "r02l_bench.json"), (2, "r02l_bench_n2.json"), (8, "r02l_bench_n8.json"))]
+if all(d for _, d in fl):
+    w("## Final build: thread-maximum selection in front of the radix select (r02l_bench*.json, r02l_select_fast_ab.jsonl)\n")
+    w("| GPUs | queries/s (ms/step) | scoring kernels / whole step vs HBM peak | select kernels per search | e2e ms | 250 searches in a row, ms/step by blocks of 50 | parity |")
+    w("|---|---|---|---|---|---|---|")
+    for n, d in fl:
+        rf = d["roofline"]
+        w(f"| {n} | {d['value']:.0f} ({d['ms_per_step']:.4f}) | {100 * rf['frac']:.1f}% / {100 * rf['whole_step_frac']:.1f}% | {rf['select_kernel_ms_per_search'] * 1e3:.1f} us | "
+          f"{d['e2e']['ms_per_step']:.3f} | {', '.join(f'{x:.3f}' for x in d['sustained']['ms_per_step_by_50'])} | {d['parity']['ok'] if d.get('parity') else '-'} |")
+    ab = jsonl("r02l_select_fast_ab.jsonl")
+    if ab:
+        a0 = next(r for r in ab if r["fast_select"] == "0")
+        a1 = next(r for r in ab if r["fast_select"] == "1" and r["threads"] == "default")
+        w(f"\nSame box, 1.25M-row shard, 64 queries (`r02l_select_fast_ab.jsonl`): radix select only {a0['search_ms']:.4f} ms per search "
+          f"({a0['select_ms_per_search'] * 1e3:.1f} us in two selects), with the thread-maximum bound {a1['search_ms']:.4f} ms ({a1['select_ms_per_search'] * 1e3:.1f} us). "
+          "The 1-GPU line above comes from a box that ran the whole bench under `sw_power_cap` (2.24 ms; 2.17-2.22 on the other boxes of the round); "
+          "8 GPUs: 0.344 -> 0.334 ms, whole step 85.4% -> 88.0% of the HBM roofline against the SCALE rehearsal below.\n")
 
 w("## Strong scaling during the round (bench lines r02c / r02d / r02e; fused exchange)\n")
 w("| GPUs | file | 64 q: queries/s (ms) | vs 1 GPU | scoring kernels / whole step vs HBM peak | e2e ms (f32 / bf16-exact queries) | 8192 q: q/s, TFLOP/s per GPU | parity |")
