@@ -38,6 +38,15 @@ for nq in ((33, 130) if small else (33, 100, 130, 300)):
     c = st.search(q, 10, mode="tensor3")                             # empty correction terms: skipped on the device
     assert np.array_equal(a[1], c[1]) and np.array_equal(a[0], c[0]) and b3[1].shape == (nq, 10)
 st.close()
+# selection paths: continuous scores (the thread-maximum bound filters and the rank sort finishes the job), top-100 and
+# top-300 (general radix path on a 256-thread CTA), many queries (small CTAs)
+xc = rng.standard_normal((n, 96)).astype(np.float32)
+st = vod_b200.CorpusStore(n, 96, dtype="bfloat16")
+st.add(xc)
+for nq, k in ((9, 100), (9, 300), (530, 100)):
+    s_c, i_c = st.search(rng.standard_normal((nq, 96)).astype(np.float32), k, mode="tensor")
+    assert (np.diff(s_c, axis=1) <= 0).all() and (i_c >= 0).all() and len(set(i_c[0].tolist())) == k
+st.close()
 ms, mi = vod_b200.merge_topk(np.stack([ref[0], ref[0]]), np.stack([ref[1], ref[1] + 100000]), 20)
 b = vod_b200.RetrievalBatch(scores=ref[0], indices=ref[1])
 m, raw = hybrid.merge_search_results({"a": b, "b": vod_b200.RetrievalBatch(scores=ref[0] * 2, indices=ref[1][:, ::-1].copy())},
