@@ -455,7 +455,8 @@ std::vector<int64_t> plan_segments(int64_t n, int cap, int k, int nq, bool safe)
   // first segment ("dump": every score stored, then one select). Measured on B200, 64 queries, k=100
   // (profiles/r02c_schedule_sweep.jsonl, after the per-query counters were spread over cache lines): 4096 rows x
   // growth 20-32, 8192 x 64, 16384 x 80-160 and 32768 x 40 are within 2% of each other on a 1.25M-row and on a
-  // 10M-row shard; 16384 rows with the widest growth has the fewest launches (2 resp. 3 segments).
+  // 10M-row shard; 16384 rows with the widest growth has the fewest launches (2 resp. 3 segments). Still the best
+  // after the selects moved to the thread-maximum bound (profiles/r02l_schedule_sweep.jsonl).
   int64_t first = round128(std::min<int64_t>(cap / 2, std::max<int64_t>(large_batch ? 4096 : 16384, 16LL * k)));
   if (large_batch) first = std::min<int64_t>(first, std::max<int64_t>(4096, round128(4LL * k)));
   // tuning knobs (development): VODB_FIRST_ROWS / VODB_GROWTH override the schedule of small batches
