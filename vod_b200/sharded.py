@@ -7,7 +7,7 @@ the contiguous row block `shard_bounds(n_total, world, rank)`; a search is
 
     local top-k on every rank (global ids = row_offset + local row, cf. sharded_search.py:103 `indices += offset`)
     -> exchange of the [B,k] scores and ids between the ranks
-    -> merge (radix select + bitonic sort on the GPU) on every rank.
+    -> merge (exact k-selection on the GPU, csrc/select.cu) on every rank.
 
 Two exchange implementations, same results:
   * exchange="p2p" (default on GPUs): fused into the kernels. The final select kernel of every rank stores its list
