@@ -723,24 +723,25 @@ struct Tc2Config {
   static constexpr int kMaxStagesRes = 12;  // resident variant: barrier slots (2 * 12 + 6 words fit the 256-byte area)
 };
 
-// RES (one term, one query tile, BN <= 128): the CTA's half of the query tile — all K chunks of it, kchunks x BN/2
-// rows x 128 B (48 KB at 64 queries x 768 dims, 96 KB at 128) — is loaded ONCE into shared memory and stays there;
-// the ring then carries corpus boxes only (10 / 7 stages of 16 KB). The L2 -> SM path, which caps these kernels at
-// ~6300 B/clk for the whole chip (B300_MICROARCH.md "LTS throughput cap"), carries the corpus bytes and nothing else:
-// 1.0x the HBM stream instead of 1.5x (64 queries, 1-CTA kernel) or 2x (128 queries).
+// RES (one query tile, BN <= 128; one term, or stacked terms): the CTA's half of the query tile — all K chunks of it,
+// kchunks x T x BN/2 rows x 128 B (48 KB at 64 one-term queries x 768 dims, 96 KB at 128, 144 KB at 64 three-term
+// queries) — is loaded ONCE into shared memory and stays there; the ring then carries corpus boxes only (10 / 7 / 4
+// stages of 16 KB). The L2 -> SM path, which caps these kernels at ~6300 B/clk for the whole chip (B300_MICROARCH.md
+// "LTS throughput cap"), carries the corpus bytes and nothing else: 1.0x the HBM stream instead of 1.5x (64 queries,
+// 1-CTA kernel), 2x (128 queries) or 1.75x (64 three-term queries streamed with the corpus).
 template <int BN, int T, bool RES = false>
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_constant__ CUtensorMap tmap_query,
                  const __grid_constant__ CUtensorMap tmap_query_last, const TcParams p) {
   using Cfg = Tc2Config<BN, T>;
-  static_assert(!RES || (T == 1 && BN <= 128), "resident queries: one term, at most 128 queries");
+  static_assert(!RES || (BN <= 128 && (T == 1 || Cfg::kConcat)), "resident queries: one tile of at most 128 queries, stacked terms");
   const int STAGES = RES ? p.n_stages : Cfg::kStages;
   constexpr int kBarSlots = RES ? Cfg::kMaxStagesRes : Cfg::kStages;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // RES: [kchunks resident query boxes][STAGES corpus boxes]; else [STAGES corpus boxes][STAGES x T query boxes]
+  // RES: [kchunks x T resident query boxes][STAGES corpus boxes]; else [STAGES corpus boxes][STAGES x T query boxes]
   unsigned char* smem_res = smem;
-  unsigned char* smem_a = RES ? smem + (size_t)p.kchunks * Cfg::kBBytes : smem;
+  unsigned char* smem_a = RES ? smem + (size_t)p.kchunks * T * Cfg::kBBytes : smem;
   unsigned char* smem_b = smem + STAGES * Cfg::kABytes;   // STAGES x T x [BN/2 x 128B] (unused when RES)
   uint64_t* bars = reinterpret_cast<uint64_t*>(RES ? smem_a + (size_t)STAGES * Cfg::kABytes : smem + STAGES * Cfg::kStageBytes);
   uint64_t* full_bar = bars;
@@ -809,10 +810,20 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
       uint32_t phase = 0;
       if (RES && n_items > 0) {
         // the CTA's half of the (only) query tile, every K chunk of it, once
-        const int q_half = (int)rank * (item_columns(p, 0, BN) / 2);
-        if (leader) mbar_expect_tx(bfull_bar, 2u * (uint32_t)p.kchunks * p.last_box_bytes);
-        for (int kc = 0; kc < p.kchunks; ++kc)
-          tma_load_2d_2sm(&tmap_query_last, bfull_bar, smem_res + (size_t)kc * Cfg::kBBytes, kc * KC, q_half, kEvictLast);
+        if constexpr (T == 1) {
+          const int q_half = (int)rank * (item_columns(p, 0, BN) / 2);
+          if (leader) mbar_expect_tx(bfull_bar, 2u * (uint32_t)p.kchunks * p.last_box_bytes);
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            tma_load_2d_2sm(&tmap_query_last, bfull_bar, smem_res + (size_t)kc * Cfg::kBBytes, kc * KC, q_half, kEvictLast);
+        } else {
+          // stacked terms: [K chunk][term][BN/2 rows], the layout one ring stage has in the streaming variant
+          const int q_half = (int)rank * (BN / 2);
+          if (leader) mbar_expect_tx(bfull_bar, 2u * (uint32_t)p.kchunks * (uint32_t)nt_run * Cfg::kBBytes);
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            for (int t = 0; t < nt_run; ++t)
+              tma_load_2d_2sm(&tmap_query, bfull_bar, smem_res + ((size_t)kc * T + t) * Cfg::kBBytes, kc * KC,
+                              t * p.q_rows_pad + q_half, kEvictLast);
+        }
       }
       for (int item = pair; item < n_items; item += n_pairs) {
         int ct, qt;
@@ -866,7 +877,7 @@ score_tc2_kernel(const __grid_constant__ CUtensorMap tmap_corpus, const __grid_c
           tcgen05_fence_after();
           const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
           if constexpr (!Cfg::kDual) {
-            const uint64_t db = make_desc_sw128(smem_u32(RES ? smem_res + (size_t)kc * Cfg::kBBytes
+            const uint64_t db = make_desc_sw128(smem_u32(RES ? smem_res + (size_t)kc * T * Cfg::kBBytes
                                                              : smem_b + (stage * T) * Cfg::kBBytes));
 #pragma unroll
             for (int k = 0; k < KC / UMMA_K; ++k)
@@ -1068,7 +1079,7 @@ template <int BN, int T, bool RES = false>
 int launch_pair(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream_t stream, int res_stages = 0) {
   using Cfg = Tc2Config<BN, T>;
   const int kchunks_all = (s->dim + KC - 1) / KC;
-  const size_t smem_bytes = RES ? (size_t)kchunks_all * Cfg::kBBytes + (size_t)res_stages * Cfg::kABytes + Cfg::kExtra
+  const size_t smem_bytes = RES ? (size_t)kchunks_all * T * Cfg::kBBytes + (size_t)res_stages * Cfg::kABytes + Cfg::kExtra
                                 : (size_t)Cfg::kSmemBytes;
   VODB_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(&score_tc2_kernel<BN, T, RES>), smem_bytes));
   const CUtensorMap* tmap_store = nullptr;
@@ -1127,13 +1138,18 @@ int launch_pair(vodb_store* s, const SegmentArgs& a, int term_policy, cudaStream
   return VODB_OK;
 }
 
-// corpus stages left for the resident-query variant (0 = the CTA's half of the query tile does not leave >= 6 of them)
-template <int BN>
-int resident_stages(const vodb_store* s) {
-  using C = Tc2Config<BN, 1>;
+// corpus stages left for the resident-query variant (0 = the CTA's half of the query tile does not leave `min_stages`)
+template <int BN, int T = 1>
+int resident_stages(const vodb_store* s, int min_stages = 6) {
+  using C = Tc2Config<BN, T>;
   const int kchunks = (s->dim + KC - 1) / KC;
-  const int st = std::min<int>(C::kMaxStagesRes, ((int)kSmemMax - (int)C::kExtra - kchunks * (int)C::kBBytes) / (int)C::kABytes);
-  return (resident_enabled() && st >= 6) ? st : 0;
+  const int st = std::min<int>(C::kMaxStagesRes, ((int)kSmemMax - (int)C::kExtra - kchunks * T * (int)C::kBBytes) / (int)C::kABytes);
+  return (resident_enabled() && st >= min_stages) ? st : 0;
+}
+// VODB_RESIDENT_TERMS=0 streams the query terms of small multi-term batches with the corpus (A/B comparisons)
+bool resident_terms_enabled() {
+  static const char* env = std::getenv("VODB_RESIDENT_TERMS");
+  return env ? (env[0] != '0') : true;
 }
 
 // one-term scan of up to 128 queries: resident-query pair kernel when it fits, else the 1-CTA kernel
@@ -1152,7 +1168,12 @@ int launch_one_term_small(vodb_store* s, const SegmentArgs& a, int term_policy, 
 // api.cu `queries_fit_store_dtype`.)
 template <int T>
 int launch_pair_terms(vodb_store* s, const SegmentArgs& a, cudaStream_t stream) {
-  if (a.nq <= 64) return launch_pair<64, T>(s, a, kTermAlways, stream);
+  if (a.nq <= 64) {
+    // all terms of the 64 queries resident (144 KB at three terms x 768 dims) when that leaves four corpus stages
+    const int st = resident_terms_enabled() ? resident_stages<64, T>(s, 4) : 0;
+    if (st > 0) return launch_pair<64, T, true>(s, a, kTermAlways, stream, st);
+    return launch_pair<64, T>(s, a, kTermAlways, stream);
+  }
   if (a.nq <= 128) return launch_pair<128, T>(s, a, kTermAlways, stream);
   int rc = launch_pair<256, 1>(s, a, kOnlyIfSingleTerm, stream);
   if (rc != VODB_OK) return rc;
