@@ -48,6 +48,7 @@ w("Files: `r02a_*` ncu of the 64-query scan of a 1.25M-row shard BEFORE the coun
   "`r02f_*` ncu raw page of the kernels beside the scan, launch list of a small-shard search; `r02g_bench.json` bench line of the "
   "final build (another box: 2.215 ms), `r02_compute_sanitizer.txt` memcheck / racecheck of the final build; "
   "`r02k_*` probes of the power-cap steps inside a loop of identical searches and of the idle gap before a search; "
+  "`r02m_*` bench lines (both arms) of the last build of the round, A/B of the resident three-term query tile; "
   "`r02l_*` the thread-maximum selection: A/B of the select time, ncu raw page of its first version, bench lines of the final build at 1 / 2 / 8 GPUs "
   "(8 GPUs without the target-shape and 8192-query sections), k = 1000 probe, 2-GPU test log; "
   "`r02j_bench.json` bench line after host-resident queries are classified on the host (e2e 2.44 ms next to a 2.22 ms device step on "
@@ -115,9 +116,9 @@ for n in (2, 4, 8):
         for run in t["runs"]) + "\n")
 
 # final build (thread-maximum selection)
-fl = [(n, line(f)) for n, f in ((1, "r02l_bench.json"), (2, "r02l_bench_n2.json"), (8, "r02l_bench_n8.json"))]
+fl = [(n, line(f)) for n, f in ((1, "r02m_bench.json"), (2, "r02l_bench_n2.json"), (8, "r02l_bench_n8.json"))]
 if all(d for _, d in fl):
-    w("## Final build: thread-maximum selection in front of the radix select (r02l_bench*.json, r02l_select_fast_ab.jsonl)\n")
+    w("## Final build: thread-maximum selection in front of the radix select (r02m_bench.json, r02l_bench_n2.json, r02l_bench_n8.json, r02l_select_fast_ab.jsonl)\n")
     w("| GPUs | queries/s (ms/step) | scoring kernels / whole step vs HBM peak | select kernels per search | e2e ms | 250 searches in a row, ms/step by blocks of 50 | parity |")
     w("|---|---|---|---|---|---|---|")
     for n, d in fl:
@@ -130,7 +131,7 @@ if all(d for _, d in fl):
         a1 = next(r for r in ab if r["fast_select"] == "1" and r["threads"] == "default")
         w(f"\nSame box, 1.25M-row shard, 64 queries (`r02l_select_fast_ab.jsonl`): radix select only {a0['search_ms']:.4f} ms per search "
           f"({a0['select_ms_per_search'] * 1e3:.1f} us in two selects), with the thread-maximum bound {a1['search_ms']:.4f} ms ({a1['select_ms_per_search'] * 1e3:.1f} us). "
-          "The 1-GPU line above comes from a box that ran the whole bench under `sw_power_cap` (2.24 ms; 2.17-2.22 on the other boxes of the round); "
+          "The 1-GPU line above comes from a box that ran the whole bench under `sw_power_cap` (2.24-2.27 ms on the last two boxes; 2.17-2.22 on the other boxes of the round, same kernels); "
           "8 GPUs: 0.344 -> 0.334 ms, whole step 85.4% -> 88.0% of the HBM roofline against the SCALE rehearsal below.\n")
 
 w("## Strong scaling during the round (bench lines r02c / r02d / r02e; fused exchange)\n")
