@@ -125,11 +125,11 @@ if all(d for _, d in fl):
         rf = d["roofline"]
         w(f"| {n} | {d['value']:.0f} ({d['ms_per_step']:.4f}) | {100 * rf['frac']:.1f}% / {100 * rf['whole_step_frac']:.1f}% | {rf['select_kernel_ms_per_search'] * 1e3:.1f} us | "
           f"{d['e2e']['ms_per_step']:.3f} | {', '.join(f'{x:.3f}' for x in d['sustained']['ms_per_step_by_50'])} | {d['parity']['ok'] if d.get('parity') else '-'} |")
-    ab = jsonl("r02l_select_fast_ab.jsonl")
+    ab = jsonl("r02m_select_fast_ab.jsonl")
     if ab:
         a0 = next(r for r in ab if r["fast_select"] == "0")
         a1 = next(r for r in ab if r["fast_select"] == "1" and r["threads"] == "default")
-        w(f"\nSame box, 1.25M-row shard, 64 queries (`r02l_select_fast_ab.jsonl`): radix select only {a0['search_ms']:.4f} ms per search "
+        w(f"\nSame box, 1.25M-row shard, 64 queries (`r02m_select_fast_ab.jsonl`): radix select only {a0['search_ms']:.4f} ms per search "
           f"({a0['select_ms_per_search'] * 1e3:.1f} us in two selects), with the thread-maximum bound {a1['search_ms']:.4f} ms ({a1['select_ms_per_search'] * 1e3:.1f} us). "
           "The 1-GPU line above comes from a box that ran the whole bench under `sw_power_cap` (2.24-2.27 ms on the last two boxes; 2.17-2.22 on the other boxes of the round, same kernels); "
           "8 GPUs: 0.344 -> 0.334 ms, whole step 85.4% -> 88.0% of the HBM roofline against the SCALE rehearsal below.\n")

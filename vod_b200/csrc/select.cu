@@ -254,34 +254,64 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
       int bin_a_i, need_b;
       find_bin_every_warp(sm.hist, k, lane, bin_a_i, need_b);
       const uint32_t bin_a = (uint32_t)bin_a_i;
-      {  // pass B: second byte, among the maxima inside bin A
-        const bool in = (lmax >> 24) == bin_a;
-        const uint32_t b = in ? ((lmax >> 16) & 255u) : 256u;
-        const unsigned peers = __match_any_sync(0xffffffffu, b);
-        if (in && lane == __ffs(peers) - 1) atomicAdd(&sm.hist[256 + b], __popc(peers));
-      }
+      // pass B: second byte, among the maxima inside bin A (the values differ from lane to lane here: plain atomics —
+      // a match over 32 distinct values costs more than the 32 conflict-free atomics it would save)
+      if ((lmax >> 24) == bin_a) atomicAdd(&sm.hist[256 + ((lmax >> 16) & 255u)], 1);
       __syncthreads();
       int bin_b, need_c;
       find_bin_every_warp(sm.hist + 256, need_b, lane, bin_b, need_c);
       const uint32_t bound = (bin_a << 24) | ((uint32_t)bin_b << 16);
       // compaction: key and list POSITION of every survivor (the id is fetched afterwards, one load per survivor and
       // all of them in flight together: loading it here would serialise an L2 round trip per survivor of a thread)
-      for (int i = tid; i < n; i += nt) {
-        const uint32_t o = key(i);
-        if (o >= bound) {
-          const int pos = atomicAdd(&sm.sel_count, 1);
-          if (pos < nt) {
-            surv_o[pos] = o;
-            surv_i[pos] = (IdxT)i;
+      for (int i0 = tid; i0 < n; i0 += 4 * nt) {  // four keys in flight, survivors are rare
+        uint32_t o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[u] = (i0 + u * nt < n) ? key(i0 + u * nt) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (o[u] >= bound && i0 + u * nt < n) {
+            const int pos = atomicAdd(&sm.sel_count, 1);
+            if (pos < nt) {
+              surv_o[pos] = o[u];
+              surv_i[pos] = (IdxT)(i0 + u * nt);
+            }
           }
         }
       }
       __syncthreads();
       const int ns = sm.sel_count;  // >= k: the k largest thread maxima are different entries
       if (ns <= nt) {
-        if (tid < ns) surv_i[tid] = load_i((int)surv_i[tid]);  // own slot only
-        __syncthreads();
-        rank_sort<IdxT>(surv_o, surv_i, ns, k, sel_o, sel_i, false);  // the first k, in output order
+        // The survivors' ids are fetched now (one load each, own slot) and needed only to order equal scores: the
+        // ranking below runs on the keys alone while the loads are in flight, and is final unless two survivors tie.
+        IdxT my_id = 0;
+        if (tid < ns) my_id = load_i((int)surv_i[tid]);
+        const int g = (ns * 8 <= nt) ? 8 : (ns * 4 <= nt) ? 4 : (ns * 2 <= nt) ? 2 : 1;
+        const int sv = tid / g, part = tid - sv * g;
+        const bool live = sv < ns;
+        const uint32_t o = live ? surv_o[sv] : 0u;
+        int rank = 0, tie = 0;
+        if (live) {
+#pragma unroll 4
+          for (int j = part; j < ns; j += g) {
+            const uint32_t oj = surv_o[j];
+            rank += (oj > o || (oj == o && j < sv)) ? 1 : 0;
+            tie |= (oj == o && j != sv) ? 1 : 0;
+          }
+        }
+        for (int off = g >> 1; off > 0; off >>= 1) {
+          rank += __shfl_xor_sync(0xffffffffu, rank, off);
+          tie |= __shfl_xor_sync(0xffffffffu, tie, off);
+        }
+        if (tid < ns) surv_i[tid] = my_id;
+        if (__syncthreads_or(tie) == 0) {
+          if (live && part == 0 && rank < k) {
+            sel_o[rank] = o;
+            sel_i[rank] = surv_i[sv];
+          }
+          __syncthreads();
+        } else {
+          rank_sort<IdxT>(surv_o, surv_i, ns, k, sel_o, sel_i, false);  // (score desc, id asc) with the ids
+        }
         sorted = true;
         n_sel = k;
         vstar = sel_o[k - 1];
