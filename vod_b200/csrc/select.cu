@@ -202,43 +202,43 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
     // thread's maximum.
     uint32_t lmax = 0u;
     {
-        int i = tid;
-        if (flat_s != nullptr && cached && ((reinterpret_cast<uintptr_t>(flat_s) | reinterpret_cast<uintptr_t>(cache)) & 15) == 0) {
-          // contiguous list (16-byte aligned): four 16-byte loads in flight per thread, 16 scores each round — the
-          // pass is latency bound (64 CTAs on 148 SMs), so memory-level parallelism is what shortens it
-          const int n4 = n >> 2;
-          const float4* src4 = reinterpret_cast<const float4*>(flat_s);
-          uint4* dst4 = reinterpret_cast<uint4*>(cache);
-          int v = tid;
-          for (; v + 3 * nt < n4; v += 4 * nt) {
-            const float4 a = src4[v], b = src4[v + nt], c = src4[v + 2 * nt], d = src4[v + 3 * nt];
-            const uint4 oa = make_uint4(ord_u32(a.x), ord_u32(a.y), ord_u32(a.z), ord_u32(a.w));
-            const uint4 ob = make_uint4(ord_u32(b.x), ord_u32(b.y), ord_u32(b.z), ord_u32(b.w));
-            const uint4 oc = make_uint4(ord_u32(c.x), ord_u32(c.y), ord_u32(c.z), ord_u32(c.w));
-            const uint4 od = make_uint4(ord_u32(d.x), ord_u32(d.y), ord_u32(d.z), ord_u32(d.w));
-            dst4[v] = oa; dst4[v + nt] = ob; dst4[v + 2 * nt] = oc; dst4[v + 3 * nt] = od;
-            lmax = max(lmax, max(max(max(oa.x, oa.y), max(oa.z, oa.w)), max(max(ob.x, ob.y), max(ob.z, ob.w))));
-            lmax = max(lmax, max(max(max(oc.x, oc.y), max(oc.z, oc.w)), max(max(od.x, od.y), max(od.z, od.w))));
-          }
-          for (; v < n4; v += nt) {
-            const float4 a = src4[v];
-            const uint4 oa = make_uint4(ord_u32(a.x), ord_u32(a.y), ord_u32(a.z), ord_u32(a.w));
-            dst4[v] = oa;
-            lmax = max(lmax, max(max(oa.x, oa.y), max(oa.z, oa.w)));
-          }
-          i = (n4 << 2) + tid;  // the last n % 4 entries go through the scalar tail below
+      int i = tid;
+      if (flat_s != nullptr && cached && ((reinterpret_cast<uintptr_t>(flat_s) | reinterpret_cast<uintptr_t>(cache)) & 15) == 0) {
+        // contiguous list (16-byte aligned): four 16-byte loads in flight per thread, 16 scores each round — the
+        // pass is latency bound (64 CTAs on 148 SMs), so memory-level parallelism is what shortens it
+        const int n4 = n >> 2;
+        const float4* src4 = reinterpret_cast<const float4*>(flat_s);
+        uint4* dst4 = reinterpret_cast<uint4*>(cache);
+        int v = tid;
+        for (; v + 3 * nt < n4; v += 4 * nt) {
+          const float4 a = src4[v], b = src4[v + nt], c = src4[v + 2 * nt], d = src4[v + 3 * nt];
+          const uint4 oa = make_uint4(ord_u32(a.x), ord_u32(a.y), ord_u32(a.z), ord_u32(a.w));
+          const uint4 ob = make_uint4(ord_u32(b.x), ord_u32(b.y), ord_u32(b.z), ord_u32(b.w));
+          const uint4 oc = make_uint4(ord_u32(c.x), ord_u32(c.y), ord_u32(c.z), ord_u32(c.w));
+          const uint4 od = make_uint4(ord_u32(d.x), ord_u32(d.y), ord_u32(d.z), ord_u32(d.w));
+          dst4[v] = oa; dst4[v + nt] = ob; dst4[v + 2 * nt] = oc; dst4[v + 3 * nt] = od;
+          lmax = max(lmax, max(max(max(oa.x, oa.y), max(oa.z, oa.w)), max(max(ob.x, ob.y), max(ob.z, ob.w))));
+          lmax = max(lmax, max(max(max(oc.x, oc.y), max(oc.z, oc.w)), max(max(od.x, od.y), max(od.z, od.w))));
         }
-        for (; i + 3 * nt < n; i += 4 * nt) {
-          float s0 = load_s(i), s1 = load_s(i + nt), s2 = load_s(i + 2 * nt), s3 = load_s(i + 3 * nt);
-          uint32_t o0 = ord_u32(s0), o1 = ord_u32(s1), o2 = ord_u32(s2), o3 = ord_u32(s3);
-          if (cached) { cache[i] = o0; cache[i + nt] = o1; cache[i + 2 * nt] = o2; cache[i + 3 * nt] = o3; }
-          lmax = max(max(lmax, o0), max(o1, max(o2, o3)));
+        for (; v < n4; v += nt) {
+          const float4 a = src4[v];
+          const uint4 oa = make_uint4(ord_u32(a.x), ord_u32(a.y), ord_u32(a.z), ord_u32(a.w));
+          dst4[v] = oa;
+          lmax = max(lmax, max(max(oa.x, oa.y), max(oa.z, oa.w)));
         }
-        for (; i < n; i += nt) {
-          uint32_t o = ord_u32(load_s(i));
-          if (cached) cache[i] = o;
-          lmax = max(lmax, o);
-        }
+        i = (n4 << 2) + tid;  // the last n % 4 entries go through the scalar tail below
+      }
+      for (; i + 3 * nt < n; i += 4 * nt) {
+        float s0 = load_s(i), s1 = load_s(i + nt), s2 = load_s(i + 2 * nt), s3 = load_s(i + 3 * nt);
+        uint32_t o0 = ord_u32(s0), o1 = ord_u32(s1), o2 = ord_u32(s2), o3 = ord_u32(s3);
+        if (cached) { cache[i] = o0; cache[i + nt] = o1; cache[i + 2 * nt] = o2; cache[i + 3 * nt] = o3; }
+        lmax = max(max(lmax, o0), max(o1, max(o2, o3)));
+      }
+      for (; i < n; i += nt) {
+        uint32_t o = ord_u32(load_s(i));
+        if (cached) cache[i] = o;
+        lmax = max(lmax, o);
+      }
     }
     if (surv_o != nullptr && (cached || smem_src) && 2 * k <= nt) {
       for (int t = tid; t < 512; t += nt) sm.hist[t] = 0;
@@ -318,104 +318,104 @@ __device__ int block_select(LoadS load_s, LoadI load_i, int n, int k, bool do_so
       }
     }
     if (!sorted) {
-    uint32_t prefix = 0u, mask = 0u;
-    int need = k;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      for (int t = tid; t < 256; t += nt) sm.hist[t] = 0;
-      __syncthreads();
-      if (shift == 24) {
-        // First radix pass. A histogram of the top byte (sign + 7 exponent bits) would send most of the list to three
-        // or four bins, and shared-memory atomics on one address cost a cycle per lane: ~8 us for a 16k-entry dump
-        // list. Scores of one query nearly always have >= k entries in the top byte of their maximum, so the pass
-        // first tries exactly that bin with ballots instead of atomics: reduce the maximum, count the entries that
-        // share its top byte. If there are at least `need` of them the k-th best lies in that bin and the pass is
-        // done; otherwise (top bin too small, e.g. one outlier score) the general histogram below runs.
-        if (tid == 0) { sm.max_ord = 0u; sm.n_top = 0; }
-        __syncthreads();
-        lmax = __reduce_max_sync(0xffffffffu, lmax);
-        if ((tid & 31) == 0) atomicMax(&sm.max_ord, lmax);
-        __syncthreads();
-        const uint32_t top = sm.max_ord >> 24;
-        int c = 0;
-        for (int j = tid; j < n; j += nt) c += (key(j) >> 24) == top ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if ((tid & 31) == 0 && c) atomicAdd(&sm.n_top, c);
-        __syncthreads();
-        if (sm.n_top >= need) {
-          if (tid == 0) { sm.bin = (int)top; sm.need = need; sm.n_eq = sm.n_top; }
-          __syncthreads();
-          prefix |= top << 24;
-          mask |= 0xffu << 24;
-          __syncthreads();
-          continue;
-        }
-        for (int j = tid; j < n; j += nt) atomicAdd(&sm.hist[key(j) >> 24], 1);
-      } else {
-        for (int i = tid; i < n; i += nt) {
-          uint32_t o = key(i);
-          if ((o & mask) == prefix) atomicAdd(&sm.hist[(o >> shift) & 255u], 1);
-        }
-      }
-      __syncthreads();
-      if (tid < 32) find_bin<true>(sm.hist, sm, need, tid);
-      __syncthreads();
-      prefix |= (uint32_t)sm.bin << shift;
-      mask |= 0xffu << shift;
-      need = sm.need;
-      __syncthreads();
-    }
-    vstar = prefix;
-    const int n_eq = sm.n_eq;
-    // ties at v*: take the `need` smallest ids
-    U istar = ~(U)0;
-    int ineed = 0x7fffffff;  // how many entries with (o==v*, id==istar) to take
-    if (n_eq > need) {
-      U iprefix = 0, imask = 0;
-      ineed = need;
-      for (int shift = (int)sizeof(U) * 8 - 8; shift >= 0; shift -= 8) {
+      uint32_t prefix = 0u, mask = 0u;
+      int need = k;
+      for (int shift = 24; shift >= 0; shift -= 8) {
         for (int t = tid; t < 256; t += nt) sm.hist[t] = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += nt) {
-          if (key(i) == vstar) {
-            U u = (U)load_i(i);
-            if ((u & imask) == iprefix) atomicAdd(&sm.hist[(int)((u >> shift) & 255u)], 1);
+        if (shift == 24) {
+          // First radix pass. A histogram of the top byte (sign + 7 exponent bits) would send most of the list to three
+          // or four bins, and shared-memory atomics on one address cost a cycle per lane: ~8 us for a 16k-entry dump
+          // list. Scores of one query nearly always have >= k entries in the top byte of their maximum, so the pass
+          // first tries exactly that bin with ballots instead of atomics: reduce the maximum, count the entries that
+          // share its top byte. If there are at least `need` of them the k-th best lies in that bin and the pass is
+          // done; otherwise (top bin too small, e.g. one outlier score) the general histogram below runs.
+          if (tid == 0) { sm.max_ord = 0u; sm.n_top = 0; }
+          __syncthreads();
+          lmax = __reduce_max_sync(0xffffffffu, lmax);
+          if ((tid & 31) == 0) atomicMax(&sm.max_ord, lmax);
+          __syncthreads();
+          const uint32_t top = sm.max_ord >> 24;
+          int c = 0;
+          for (int j = tid; j < n; j += nt) c += (key(j) >> 24) == top ? 1 : 0;
+          c = __reduce_add_sync(0xffffffffu, c);
+          if ((tid & 31) == 0 && c) atomicAdd(&sm.n_top, c);
+          __syncthreads();
+          if (sm.n_top >= need) {
+            if (tid == 0) { sm.bin = (int)top; sm.need = need; sm.n_eq = sm.n_top; }
+            __syncthreads();
+            prefix |= top << 24;
+            mask |= 0xffu << 24;
+            __syncthreads();
+            continue;
+          }
+          for (int j = tid; j < n; j += nt) atomicAdd(&sm.hist[key(j) >> 24], 1);
+        } else {
+          for (int i = tid; i < n; i += nt) {
+            uint32_t o = key(i);
+            if ((o & mask) == prefix) atomicAdd(&sm.hist[(o >> shift) & 255u], 1);
           }
         }
         __syncthreads();
-        if (tid < 32) find_bin<false>(sm.hist, sm, ineed, tid);
+        if (tid < 32) find_bin<true>(sm.hist, sm, need, tid);
         __syncthreads();
-        iprefix |= (U)sm.bin << shift;
-        imask |= (U)0xff << shift;
-        ineed = sm.need;
+        prefix |= (uint32_t)sm.bin << shift;
+        mask |= 0xffu << shift;
+        need = sm.need;
         __syncthreads();
       }
-      istar = iprefix;
-    }
-    if (tid == 0) {
-      sm.sel_count = 0;
-      sm.dup_taken = 0;
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += nt) {
-      uint32_t o = key(i);
-      if (o < vstar) continue;
-      IdxT id = load_i(i);
-      bool take = o > vstar;
-      if (!take) {
-        U u = (U)id;
-        if (u < istar) take = true;
-        else if (u == istar) take = atomicAdd(&sm.dup_taken, 1) < ineed;
+      vstar = prefix;
+      const int n_eq = sm.n_eq;
+      // ties at v*: take the `need` smallest ids
+      U istar = ~(U)0;
+      int ineed = 0x7fffffff;  // how many entries with (o==v*, id==istar) to take
+      if (n_eq > need) {
+        U iprefix = 0, imask = 0;
+        ineed = need;
+        for (int shift = (int)sizeof(U) * 8 - 8; shift >= 0; shift -= 8) {
+          for (int t = tid; t < 256; t += nt) sm.hist[t] = 0;
+          __syncthreads();
+          for (int i = tid; i < n; i += nt) {
+            if (key(i) == vstar) {
+              U u = (U)load_i(i);
+              if ((u & imask) == iprefix) atomicAdd(&sm.hist[(int)((u >> shift) & 255u)], 1);
+            }
+          }
+          __syncthreads();
+          if (tid < 32) find_bin<false>(sm.hist, sm, ineed, tid);
+          __syncthreads();
+          iprefix |= (U)sm.bin << shift;
+          imask |= (U)0xff << shift;
+          ineed = sm.need;
+          __syncthreads();
+        }
+        istar = iprefix;
       }
-      if (take) {
-        int pos = atomicAdd(&sm.sel_count, 1);
-        if (pos < P) {
-          sel_o[pos] = o;
-          sel_i[pos] = id;
+      if (tid == 0) {
+        sm.sel_count = 0;
+        sm.dup_taken = 0;
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += nt) {
+        uint32_t o = key(i);
+        if (o < vstar) continue;
+        IdxT id = load_i(i);
+        bool take = o > vstar;
+        if (!take) {
+          U u = (U)id;
+          if (u < istar) take = true;
+          else if (u == istar) take = atomicAdd(&sm.dup_taken, 1) < ineed;
+        }
+        if (take) {
+          int pos = atomicAdd(&sm.sel_count, 1);
+          if (pos < P) {
+            sel_o[pos] = o;
+            sel_i[pos] = id;
+          }
         }
       }
-    }
-    __syncthreads();
-    n_sel = min(sm.sel_count, k);
+      __syncthreads();
+      n_sel = min(sm.sel_count, k);
     }  // !sorted
   }
 
