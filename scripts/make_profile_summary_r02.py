@@ -48,7 +48,7 @@ w("Files: `r02a_*` ncu of the 64-query scan of a 1.25M-row shard BEFORE the coun
   "`r02f_*` ncu raw page of the kernels beside the scan, launch list of a small-shard search; `r02g_bench.json` bench line of the "
   "final build (another box: 2.215 ms), `r02_compute_sanitizer.txt` memcheck / racecheck of the final build; "
   "`r02k_*` probes of the power-cap steps inside a loop of identical searches and of the idle gap before a search; "
-  "`r02m_*` bench lines (both arms) of the last build of the round, A/B of the resident three-term query tile; "
+  "`r02m_*` bench lines (both arms) of the last build of the round, launch list of the bench command and ncu raw page of its select kernels, A/B of the resident three-term query tile; "
   "`r02l_*` the thread-maximum selection: A/B of the select time, ncu raw page of its first version, bench lines of the final build at 1 / 2 / 8 GPUs "
   "(8 GPUs without the target-shape and 8192-query sections), k = 1000 probe, 2-GPU test log; "
   "`r02j_bench.json` bench line after host-resident queries are classified on the host (e2e 2.44 ms next to a 2.22 ms device step on "
@@ -133,6 +133,35 @@ if all(d for _, d in fl):
           f"({a0['select_ms_per_search'] * 1e3:.1f} us in two selects), with the thread-maximum bound {a1['search_ms']:.4f} ms ({a1['select_ms_per_search'] * 1e3:.1f} us). "
           "The 1-GPU line above comes from a box that ran the whole bench under `sw_power_cap` (2.24-2.27 ms on the last two boxes; 2.17-2.22 on the other boxes of the round, same kernels); "
           "8 GPUs: 0.344 -> 0.334 ms, whole step 85.4% -> 88.0% of the HBM roofline against the SCALE rehearsal below.\n")
+
+def _launch_rows(name):
+    import csv as _c, re as _r
+    f = P / name
+    if not f.exists():
+        return []
+    rows = list(_c.reader(f.open()))
+    h = next((i for i, r in enumerate(rows) if r and r[0] == "ID"), None)
+    if h is None:
+        return []
+    hd = rows[h]
+    ki, vi = hd.index("Kernel Name"), hd.index("Metric Value")
+    out_ = []
+    for r in rows[h + 1:]:
+        if len(r) == len(hd):
+            m = _r.search(r"(\w+_kernel(?:<[^(]*?>)?)\(", r[ki])
+            out_.append((m.group(1) if m else r[ki][:40], float(r[vi]) / 1e3))
+    return out_
+_lr = _launch_rows("r02m_launches_ncu.csv")
+_starts = [i for i, (k_, _) in enumerate(_lr) if k_.startswith("prepare_kernel")]
+if len(_starts) >= 5:
+    seq = _lr[_starts[3]:_starts[4]]
+    tot = sum(us for _, us in seq)
+    w("## One search of the bench command, final build, per launch (r02m_launches_ncu.csv: `ncu --metrics gpu__time_duration.sum` over `bench.py --steps 2 --warmup 1`; cold cache, serialised)\n")
+    w("| kernel | us | share |\n|---|---|---|")
+    for k_, us in seq:
+        w(f"| `{k_}` | {us:.1f} | {100 * us / tot:.1f}% |")
+    w(f"\nScoring kernels {100 * sum(us for k_, us in seq if k_.startswith('score')) / tot:.1f}% of the search (CUDA events in the bench line: "
+      "`roofline.score_kernel_ms_per_search` / `ms_per_step`, same share); the selects were 18-20 us each before the thread-maximum bound (r02c_launches_ncu.csv).\n")
 
 w("## Strong scaling during the round (bench lines r02c / r02d / r02e; fused exchange)\n")
 w("| GPUs | file | 64 q: queries/s (ms) | vs 1 GPU | scoring kernels / whole step vs HBM peak | e2e ms (f32 / bf16-exact queries) | 8192 q: q/s, TFLOP/s per GPU | parity |")
